@@ -1,0 +1,258 @@
+"""Per-rank training engine (the body of a barrier task).
+
+Replaces the reference's Python hot loop (distributed.py:140-203; call stack in
+SURVEY.md §3.1).  Differences by design:
+
+* one flat gradient arena → ONE collective (or one fused P2P kernel) per step,
+  loss and stop vote piggy-backed in the same payload (no extra all-reduces,
+  reference distributed.py:188,194);
+* labels get their dtype once, from the criterion (quirk Q3);
+* mini-batches are sampled on the training device (quirk Q2/G12);
+* validation runs under ``no_grad`` in eval mode (quirk Q6);
+* rank 0's initial weights are broadcast (quirk Q7), float buffers averaged at
+  the end (quirk Q8), only rank 0 ships a state_dict back (quirk Q14);
+* the per-step loss history is returned to the driver (the reference drops it).
+
+Two step implementations share this loop:
+
+* ``EagerStep``  – autograd over the user's module (any ``nn.Module``), CPU or
+  GPU, with our Linear/Conv2d/CE kernels swapped in on B200 when available;
+* ``FusedMLPStep`` (runtime/fused_mlp.py) – recognised MLP + CE/MSE + Adam/SGD
+  runs as a CUDA graph of hand-written sm_100a kernels, no autograd, no Python
+  in the loop.
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from sparktorch_b200.runtime.flat import FlatArena
+from sparktorch_b200.runtime.optim import OptSpec, parse_optimizer
+from sparktorch_b200.util import criterion_wants_class_index, split_validation
+
+
+@dataclasses.dataclass
+class TrainConfig:
+    iters: int = 10
+    mini_batch: int = -1
+    validation_pct: float = 0.0
+    early_stop_patience: int = -1
+    verbose: int = 0
+    device: str = "cpu"
+    precision: str = "auto"       # auto | fp32 | bf16
+    engine: str = "auto"          # auto | eager | fused
+    comm: str = "auto"            # auto | collective | p2p
+    seed: Optional[int] = None
+    streaming: bool = False       # keep the partition in pinned host memory, H2D one batch per step
+
+
+@dataclasses.dataclass
+class FitResult:
+    state_dict: Optional[Dict[str, torch.Tensor]]
+    history: Dict[str, Any]
+
+
+def resolve_device(device: str, local_index: int) -> torch.device:
+    if device is None or str(device) == "cpu":
+        return torch.device("cpu")
+    if str(device).startswith("cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("device='cuda' requested but no CUDA device is visible in this task")
+        if ":" in str(device):
+            return torch.device(device)
+        return torch.device("cuda", local_index % torch.cuda.device_count())
+    return torch.device(device)
+
+
+def prepare_targets(Y: Optional[torch.Tensor], criterion) -> Optional[torch.Tensor]:
+    if Y is None:
+        return None
+    if criterion_wants_class_index(criterion):
+        return Y.reshape(-1).long()
+    return Y
+
+
+class EagerStep:
+    """fwd → loss → bwd on the user's module; gradients land in the arena."""
+
+    name = "eager"
+
+    def __init__(self, model: nn.Module, criterion, arena: FlatArena):
+        self.model, self.criterion, self.arena = model, criterion, arena
+
+    def run(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.arena.zero_grad()
+        out = self.model(x)
+        loss = self.criterion(out, y)
+        loss.backward()
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            return self.criterion(self.model(x), y).detach()
+        finally:
+            self.model.train(was_training)
+
+
+class DeviceSampler:
+    """Mini-batch index sampler living on the training device (no host sync)."""
+
+    def __init__(self, n: int, batch: int, device: torch.device, seed: Optional[int]):
+        self.n, self.batch = n, batch
+        self.gen = torch.Generator(device=device)
+        if seed is not None:
+            self.gen.manual_seed(seed)
+        else:
+            self.gen.seed()
+        self.device = device
+
+    def next(self) -> torch.Tensor:
+        # without replacement inside a batch, independent across steps (reference
+        # semantics: np.random.choice(n, mb, replace=False), distributed.py:146)
+        return torch.randperm(self.n, device=self.device, generator=self.gen)[: self.batch]
+
+
+def build_comm(arena: FlatArena, spec: OptSpec, user_opt, cfg: TrainConfig, world: int, device: torch.device):
+    from sparktorch_b200.parallel.comm import CollectiveComm, LocalComm
+
+    patience = cfg.early_stop_patience
+    want_p2p = cfg.comm in ("auto", "p2p") and device.type == "cuda" and spec.kind != "other"
+    if want_p2p:
+        try:
+            from sparktorch_b200.parallel.p2p import P2PFusedComm
+
+            return P2PFusedComm(arena, spec, patience=patience, world=world)
+        except Exception:
+            if cfg.comm == "p2p":
+                raise
+    if world == 1:
+        return LocalComm(arena, spec, user_opt, patience)
+    return CollectiveComm(arena, spec, user_opt, patience)
+
+
+def train_partition(
+    rank: int,
+    world: int,
+    model: nn.Module,
+    criterion,
+    opt_cls,
+    opt_params: Optional[Dict],
+    X: np.ndarray,
+    Y: Optional[np.ndarray],
+    cfg: TrainConfig,
+    device: torch.device,
+) -> FitResult:
+    """Train one replica on its partition; returns rank 0's weights + history."""
+    t_start = time.time()
+    seed = cfg.seed
+    rng = np.random.default_rng(None if seed is None else seed + 7919 * rank)
+
+    # ---- fused path (recognised MLP on B200) --------------------------------
+    if cfg.engine in ("auto", "fused") and device.type == "cuda":
+        try:
+            from sparktorch_b200.runtime.fused_mlp import try_fused_fit
+
+            res = try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg, device, rng)
+            if res is not None:
+                return res
+            if cfg.engine == "fused":
+                raise RuntimeError("engine='fused' requested but the model/criterion/optimizer is not lowerable")
+        except ImportError:
+            if cfg.engine == "fused":
+                raise
+
+    # ---- data ---------------------------------------------------------------
+    xt = torch.from_numpy(X)
+    yt = torch.from_numpy(Y) if Y is not None else None
+    x_val = y_val = None
+    if cfg.validation_pct > 0:
+        tr, va = split_validation(X.shape[0], cfg.validation_pct, rng)
+        if len(va) > 0:
+            x_val = xt[torch.from_numpy(va)]
+            y_val = yt[torch.from_numpy(va)] if yt is not None else None
+            xt = xt[torch.from_numpy(tr)]
+            yt = yt[torch.from_numpy(tr)] if yt is not None else None
+    x_all = xt.to(device)
+    y_all = prepare_targets(yt.to(device), criterion) if yt is not None else x_all
+    if x_val is not None:
+        x_val = x_val.to(device)
+        y_val = prepare_targets(y_val.to(device), criterion) if y_val is not None else x_val
+
+    # ---- model / arena / comm ----------------------------------------------
+    model = model.to(device)
+    model.train()
+    if hasattr(criterion, "to"):
+        criterion = criterion.to(device)
+    if device.type == "cuda" and cfg.engine != "eager_plain":
+        try:  # swap in our sm_100a Linear/Conv2d/CE autograd functions where they apply
+            from sparktorch_b200.ops.module_swap import swap_modules
+
+            model, criterion = swap_modules(model, criterion, precision=cfg.precision)
+        except ImportError:
+            pass
+    arena = FlatArena(model, device)
+    spec = parse_optimizer(opt_cls, opt_params)
+    user_opt = None
+    if spec.kind == "other":
+        user_opt = opt_cls(arena.params, **opt_params) if opt_params else opt_cls(arena.params)
+    comm = build_comm(arena, spec, user_opt, cfg, world, device)
+    comm.broadcast_params()
+    step = EagerStep(model, criterion, arena)
+
+    n = x_all.shape[0]
+    use_mb = 0 < cfg.mini_batch < n
+    sampler = DeviceSampler(n, cfg.mini_batch, device, None if seed is None else seed + rank) if use_mb else None
+    has_es = cfg.early_stop_patience > 0
+    need_loss = bool(cfg.verbose) or has_es
+    losses: List[float] = []
+    loss_buf = torch.zeros(max(cfg.iters, 1), dtype=torch.float32, device=device)
+    stopped_at = None
+    t_loop = time.time()
+
+    for i in range(cfg.iters):
+        if sampler is not None:
+            idx = sampler.next()
+            xb, yb = x_all[idx], (y_all[idx] if y_all is not x_all else None)
+            if yb is None:
+                yb = xb
+        else:
+            xb, yb = x_all, y_all
+        loss = step.run(xb, yb)
+        val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
+        # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
+        arena.tail[0] = val_loss if val_loss is not None else loss
+        loss_buf[i] = loss
+        res = comm.reduce_and_update(need_loss)
+        if cfg.verbose:
+            print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {res.loss} "
+                  f"Partition Training Loss: {float(loss)}, "
+                  f"Partition Validation Loss: {None if val_loss is None else float(val_loss)}")
+        if res.stop:
+            stopped_at = i
+            break
+    comm.finish()
+    n_done = cfg.iters if stopped_at is None else stopped_at + 1
+    losses = loss_buf[:n_done].detach().cpu().tolist()
+    comm.average_buffers(model)
+    t_end = time.time()
+    history = {
+        "engine": step.name,
+        "comm": type(comm).__name__,
+        "world_size": world,
+        "train_loss": losses,
+        "stopped_at": stopped_at,
+        "iters_run": n_done,
+        "samples_per_step": (cfg.mini_batch if use_mb else n) * world,
+        "loop_seconds": t_end - t_loop,
+        "total_seconds": t_end - t_start,
+    }
+    state = arena.detach_state_dict() if rank == 0 else None
+    return FitResult(state, history)
