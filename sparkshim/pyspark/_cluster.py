@@ -49,6 +49,12 @@ def _free_port() -> int:
     return port
 
 
+def under_torchrun() -> bool:
+    """True when this process is one rank of a ``torch.distributed.run`` job."""
+    return (int(os.environ.get("WORLD_SIZE", "1")) > 1 and "RANK" in os.environ
+            and ("TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ))
+
+
 def bind_gpu(slot: int) -> None:
     """Executor → GPU assignment (only if torch+CUDA are present)."""
     try:
@@ -113,7 +119,7 @@ class _Slot:
 class LocalCluster:
     def __init__(self, n_slots: int):
         self.n_slots = max(1, int(n_slots))
-        self.mode = "torchrun" if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "RANK" in os.environ else "spawn"
+        self.mode = "torchrun" if under_torchrun() else "spawn"
         self._slots: dict[int, _Slot] = {}
         self._listener: Optional[Listener] = None
         self._port: Optional[int] = None
@@ -296,8 +302,15 @@ def _store():
     )
 
 
+def _detach_from_agent_store() -> None:
+    """Tasks create their own process groups on their own ports; they must not
+    be redirected to torchrun's agent store (which only exists on MASTER_PORT)."""
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+
+
 def _publish_port(port: int) -> None:
     _store().set("sparkshim/driver_port", str(port))
+    _detach_from_agent_store()
 
 
 def serve_as_executor_rank() -> None:
@@ -305,6 +318,7 @@ def serve_as_executor_rank() -> None:
     from pyspark import _worker
 
     port = int(_store().get("sparkshim/driver_port").decode())
+    _detach_from_agent_store()
     slot = int(os.environ["RANK"])
     _worker.serve("127.0.0.1", port, slot)
     sys.exit(0)

@@ -37,9 +37,9 @@ class _Builder:
         if SparkSession._active is not None:
             return SparkSession._active
         # under torch.distributed.run the non-zero ranks are the executors
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("RANK", "0")) != 0:
-            from pyspark._cluster import serve_as_executor_rank
+        from pyspark._cluster import serve_as_executor_rank, under_torchrun
 
+        if under_torchrun() and int(os.environ.get("RANK", "0")) != 0:
             serve_as_executor_rank()  # never returns
         master = self._master or os.environ.get("SPARKSHIM_MASTER", "local[*]")
         sc = SparkContext._active_spark_context or SparkContext(master, self._name, SparkConf(self._conf))

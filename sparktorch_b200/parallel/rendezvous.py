@@ -10,7 +10,6 @@ hard-codes gloo even for CUDA tensors), ``gloo`` on CPU.
 from __future__ import annotations
 
 import datetime
-import os
 import socket
 from typing import Tuple
 
@@ -50,20 +49,16 @@ def init_from_barrier(context, device: torch.device) -> Tuple[int, int]:
         dist.destroy_process_group()
     if world == 1:
         return 0, 1
-    os.environ["MASTER_ADDR"] = str(addrs[0])
-    os.environ["MASTER_PORT"] = str(share_port(addrs[0], context))
-    os.environ["WORLD_SIZE"] = str(world)
-    os.environ["RANK"] = str(rank)
-    os.environ["NODE_RANK"] = str(rank)
-    # torch.distributed.run exports this for its own agent store; our group has its own port
-    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+    port = share_port(addrs[0], context)
     kwargs = {}
     if device.type == "cuda":
         backend = "nccl"
         kwargs["device_id"] = device
     else:
         backend = "gloo"
-    dist.init_process_group(backend, rank=rank, world_size=world,
+    # tcp:// rendezvous: nothing is written to os.environ (the driver process
+    # hosts task 0 inline and must not inherit a stale WORLD_SIZE/RANK)
+    dist.init_process_group(backend, init_method=f"tcp://{addrs[0]}:{port}", rank=rank, world_size=world,
                             timeout=datetime.timedelta(seconds=600), **kwargs)
     return rank, world
 

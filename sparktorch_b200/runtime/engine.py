@@ -49,6 +49,7 @@ class TrainConfig:
     comm: str = "auto"            # auto | collective | p2p
     seed: Optional[int] = None
     streaming: bool = False       # keep the partition in pinned host memory, H2D one batch per step
+    time_window: Optional[Tuple[int, int]] = None   # (first_step, n_steps): device-time this window (bench/profiling)
 
 
 @dataclasses.dataclass
@@ -75,6 +76,56 @@ def prepare_targets(Y: Optional[torch.Tensor], criterion) -> Optional[torch.Tens
     if criterion_wants_class_index(criterion):
         return Y.reshape(-1).long()
     return Y
+
+
+class WindowTimer:
+    """Device-times steps [first, first+n): barrier + synchronize on both sides,
+    CUDA events on the compute stream, MAX over ranks."""
+
+    def __init__(self, window, device: torch.device, world: int):
+        self.window, self.device, self.world = window, device, world
+        self.ms = None
+        self._t0 = None
+        if window is not None and device.type == "cuda":
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def before_step(self, i: int) -> None:
+        if self.window is not None and i == self.window[0]:
+            self._sync()
+            self._t0 = time.perf_counter()
+            if self.device.type == "cuda":
+                self.e0.record()
+
+    def after_step(self, i: int) -> None:
+        if self.window is not None and i == self.window[0] + self.window[1] - 1:
+            if self.device.type == "cuda":
+                self.e1.record()
+                torch.cuda.synchronize(self.device)
+                ms = self.e0.elapsed_time(self.e1)
+            else:
+                ms = (time.perf_counter() - self._t0) * 1e3
+            wall = (time.perf_counter() - self._t0) * 1e3
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self.ms = (float(t[0]), float(t[1]))
+            self._sync()
+
+    def result_ms(self):
+        return None if self.ms is None else {"device_ms": self.ms[0], "wall_ms": self.ms[1]}
 
 
 class EagerStep:
@@ -180,8 +231,13 @@ def train_partition(
             y_val = yt[torch.from_numpy(va)] if yt is not None else None
             xt = xt[torch.from_numpy(tr)]
             yt = yt[torch.from_numpy(tr)] if yt is not None else None
-    x_all = xt.to(device)
-    y_all = prepare_targets(yt.to(device), criterion) if yt is not None else x_all
+    stream_host = cfg.streaming and device.type == "cuda" and 0 < cfg.mini_batch < xt.shape[0]
+    if stream_host:       # partition stays in pinned host memory; one batch is copied per step
+        x_all = xt.pin_memory()
+        y_all = prepare_targets(yt, criterion).pin_memory() if yt is not None else x_all
+    else:
+        x_all = xt.to(device)
+        y_all = prepare_targets(yt.to(device), criterion) if yt is not None else x_all
     if x_val is not None:
         x_val = x_val.to(device)
         y_val = prepare_targets(y_val.to(device), criterion) if y_val is not None else x_val
@@ -209,7 +265,12 @@ def train_partition(
 
     n = x_all.shape[0]
     use_mb = 0 < cfg.mini_batch < n
-    sampler = DeviceSampler(n, cfg.mini_batch, device, None if seed is None else seed + rank) if use_mb else None
+    sampler = None
+    if use_mb and not stream_host:
+        sampler = DeviceSampler(n, cfg.mini_batch, device, None if seed is None else seed + rank)
+    window = WindowTimer(cfg.time_window, device, world)
+    host_loss = torch.zeros(max(cfg.iters, 1), dtype=torch.float32).pin_memory() if stream_host else None
+    h2d_bytes = d2h_bytes = 0
     has_es = cfg.early_stop_patience > 0
     need_loss = bool(cfg.verbose) or has_es
     losses: List[float] = []
@@ -218,7 +279,14 @@ def train_partition(
     t_loop = time.time()
 
     for i in range(cfg.iters):
-        if sampler is not None:
+        window.before_step(i)
+        if stream_host:
+            # sequential sweep over the (already shuffled) pinned partition
+            lo = (i * cfg.mini_batch) % (n - cfg.mini_batch + 1)
+            xb = x_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
+            yb = xb if y_all is x_all else y_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
+            h2d_bytes = xb.numel() * xb.element_size() + (0 if yb is xb else yb.numel() * yb.element_size())
+        elif sampler is not None:
             idx = sampler.next()
             xb, yb = x_all[idx], (y_all[idx] if y_all is not x_all else None)
             if yb is None:
@@ -231,6 +299,10 @@ def train_partition(
         arena.tail[0] = val_loss if val_loss is not None else loss
         loss_buf[i] = loss
         res = comm.reduce_and_update(need_loss)
+        if host_loss is not None:     # per-step device→host read of the step result
+            host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+            d2h_bytes = 4
+        window.after_step(i)
         if cfg.verbose:
             print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {res.loss} "
                   f"Partition Training Loss: {float(loss)}, "
@@ -252,6 +324,10 @@ def train_partition(
         "iters_run": n_done,
         "samples_per_step": (cfg.mini_batch if use_mb else n) * world,
         "loop_seconds": t_end - t_loop,
+        "window_ms": window.result_ms(),
+        "h2d_bytes_per_step": h2d_bytes,
+        "d2h_bytes_per_step": d2h_bytes,
+        "streaming": bool(stream_host),
         "total_seconds": t_end - t_start,
     }
     state = arena.detach_state_dict() if rank == 0 else None

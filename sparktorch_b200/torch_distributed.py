@@ -266,7 +266,8 @@ class SparkTorch(Estimator, HasInputCol, HasPredictionCol, HasLabelCol, PysparkR
                 rdd=rdd, torch_obj=torch_obj, iters=self.getIters(), partition_shuffles=1,
                 verbose=self.getVerbose(), mini_batch=self.getMiniBatch(), validation_pct=self.getValidationPct(),
                 device=device, early_stop_patience=self.getEarlyStopPatience(), compile_mode=self.getCompileMode(),
-                precision=precision, engine=engine, seed=seed, streaming=streaming, return_history=True)
+                precision=precision, engine=engine, seed=seed, streaming=streaming, return_history=True,
+                time_window=getattr(self, "_time_window", None))
         elif mode == "hogwild":
             from sparktorch_b200.hogwild import get_main, train
             from sparktorch_b200.server import Server
