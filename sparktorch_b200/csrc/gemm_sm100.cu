@@ -1,0 +1,355 @@
+// bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM),
+// operands staged by TMA (SWIZZLE_128B), warp-specialised:
+//
+//     D[M,N] = alpha * sum_k A[M,K] * B[N,K]        (A and B both K-major)
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  : epilogue – tcgen05.ld the accumulator, apply the fused
+//                 epilogue and store straight from registers.
+//
+// Fused epilogue (all optional, runtime selected): + bias[n], ReLU, multiply by
+// (mask_src[m,n] > 0) (= ReLU backward), row-major bf16 store, TRANSPOSED bf16
+// store (feeds the next K-major GEMM without a transpose kernel), row-major or
+// transposed fp32 store / red.add (split-K, gradient arena), column sums over m
+// (bias gradients) with one red.add per column.
+//
+// This covers every GEMM of Linear fwd / dgrad / wgrad (reference hot ops G1, G2,
+// G3) – the reference runs cuBLAS sgemm + separate ATen
+// bias/ReLU/threshold_backward/sum kernels for the same work.
+#include "common.cuh"
+#include "gemm_sm100.h"
+
+namespace st {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (STAGE_BYTES * 8 <= 200 * 1024) ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+// A_MN / B_MN: the operand is stored "MN-major" = [K rows, M|N contiguous] (e.g. the
+// activations [batch, features] when the reduction runs over the batch, or a weight
+// [out, in] used as the B operand of dgrad).  TMA then brings 64-wide (128 B) column
+// slabs of BLOCK_K rows; the UMMA descriptor walks them with LBO = slab size and
+// SBO = 1024 B (8 K-rows), and each UMMA_K=16 step advances by 16 rows = 2048 B.
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmEpilogue ep, int M, int N, int K, int k_blocks_per_split) {
+  using S = GemmSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = blockIdx.z * k_blocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + k_blocks_per_split);
+  const int num_kb = kb_end - kb_begin;   // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % S::STAGES;
+        const uint32_t ph = (i / S::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::STAGE_BYTES;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        if constexpr (A_MN) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + 64 * j, k0);
+        } else {
+          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
+        }
+        if constexpr (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + 64 * j, k0);
+        } else {
+          tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N < 16 ? 16 : BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % S::STAGES;
+        const uint32_t ph = (i / S::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
+        const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
+        // per UMMA_K=16 step, in units of 16 B of the start-address field:
+        //   K-major : 16 bf16 = 32 B inside the swizzled 128 B row -> +2
+        //   MN-major: 16 K-rows of 128 B = 2048 B                  -> +128
+        constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          umma_f16(tmem_base, da + ka * k, db + kb * k, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+      const int col0 = n0 + c0;
+      if (col0 >= N) break;                    // warp-uniform
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0);
+      if constexpr (CHUNK == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
+      // overlap: fetch the mask tile row while the TMEM load is in flight
+      uint4 mk[4];
+      const bool full_chunk = (col0 + CHUNK <= N);
+      const bool vec_ok = full_chunk;          // leading dims are multiples of 8 elements, col0 multiple of 16
+      if (ep.mask_src != nullptr && row_ok && vec_ok) {
+        const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + size_t(row) * ep.ld_mask + col0);
+#pragma unroll
+        for (int v = 0; v < CHUNK / 8; ++v) mk[v] = mp[v];
+      }
+      tmem_ld_wait();
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {
+        float v = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.bias != nullptr && col0 + j < N) v += ep.bias[col0 + j];
+        if (ep.relu) v = fmaxf(v, 0.f);
+        acc[j] = v;
+      }
+      if (ep.mask_src != nullptr) {
+        if (row_ok && vec_ok) {
+          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(mk);
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) acc[j] = (__bfloat162float(mb[j]) > 0.f) ? acc[j] : 0.f;
+        } else if (row_ok) {
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) acc[j] = (__bfloat162float(ep.mask_src[size_t(row) * ep.ld_mask + col0 + j]) > 0.f) ? acc[j] : 0.f;
+        }
+      }
+      if (!row_ok) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) acc[j] = 0.f;
+      }
+      // ---- row-major bf16
+      if (ep.out_bf16 != nullptr && row_ok) {
+        __nv_bfloat16* op = ep.out_bf16 + size_t(row) * ep.ld_out + col0;
+        if (vec_ok) {
+#pragma unroll
+          for (int v = 0; v < CHUNK / 8; ++v) {
+            uint4 w;
+            w.x = pack_bf16x2(acc[8 * v + 0], acc[8 * v + 1]);
+            w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
+            w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]);
+            w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
+            reinterpret_cast<uint4*>(op)[v] = w;
+          }
+        } else {
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) op[j] = __float2bfloat16(acc[j]);
+        }
+      }
+      // ---- row-major fp32 (store or red.add for split-K)
+      if (ep.out_f32 != nullptr && row_ok) {
+        float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
+        if (ep.atomic_f32) {
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) red_add_f32(op + j, acc[j]);
+        } else if (vec_ok && (ep.ld_f32 & 3) == 0) {
+#pragma unroll
+          for (int v = 0; v < CHUNK / 4; ++v)
+            reinterpret_cast<float4*>(op)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        } else {
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) op[j] = acc[j];
+        }
+      }
+      // ---- transposed stores: lanes hold consecutive rows -> coalesced along m
+      if (ep.out_t_bf16 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          if (col0 + j < N && row_ok) ep.out_t_bf16[size_t(col0 + j) * ep.ld_out_t + row] = __float2bfloat16(acc[j]);
+        }
+      }
+      if (ep.out_t_f32 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          if (col0 + j < N && row_ok) {
+            float* op = ep.out_t_f32 + size_t(col0 + j) * ep.ld_f32_t + row;
+            if (ep.atomic_f32) red_add_f32(op, acc[j]); else *op = acc[j];
+          }
+        }
+      }
+      // ---- column sums over the 32 rows of this warp (bias gradient)
+      if (ep.colsum != nullptr) {
+        // butterfly: after the 5 rounds lane L holds sum over lanes of column L (31 shuffles per 32 columns)
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j < CHUNK) ? acc[j] : 0.f;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+          const bool up = (lane & s) != 0;
+#pragma unroll
+          for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, v[0]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix with `rows` rows of `cols` contiguous elements (pitch ld); box = box_rows x 64 cols,
+// 128B swizzle, out-of-bounds elements read as 0.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : int(r);
+}
+
+int gemm_pick_block_n(int N, int b_mn) {
+  if (!b_mn) {
+    if (N <= 16) return 16;
+    if (N <= 32) return 32;
+  }
+  if (N <= 64) return 64;
+  return 128;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                             int split_k, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int kb_per = (total_kb + split_k - 1) / split_k;
+  int splits = (total_kb + kb_per - 1) / kb_per;      // no empty splits
+  dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, splits);
+  gemm_bf16_tn_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, ep, M, N, K, kb_per);
+  return cudaGetLastError();
+}
+
+template <bool A_MN, bool B_MN>
+static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
+                               int N, int K, int split_k, cudaStream_t stream) {
+  switch (block_n) {
+    case 16: if constexpr (!B_MN) return launch_bn<16, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream); break;
+    case 32: if constexpr (!B_MN) return launch_bn<32, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream); break;
+    case 64: return launch_bn<64, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
+    case 128: return launch_bn<128, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
+    case 256: return launch_bn<256, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// D[M,N] = A * B^T.  a_mn=0: A stored [M,K] (pitch lda); a_mn=1: A stored [K,M].  Same for B with N.
+// bf16, base pointers 16-byte aligned, pitches multiples of 8 elements.
+int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+              const GemmEpilogue* ep, int block_n, int split_k, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -2;
+  if (block_n <= 0) block_n = gemm_pick_block_n(N, b_mn);
+  if (b_mn && block_n < 64) block_n = 64;
+  if (split_k <= 0) split_k = 1;
+  if (split_k > 1 && !ep->atomic_f32) return -3;
+  CUtensorMap ta, tb;
+  int rc = a_mn ? make_tmap_bf16_2d(&ta, A, K, M, lda, BLOCK_K) : make_tmap_bf16_2d(&ta, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = b_mn ? make_tmap_bf16_2d(&tb, B, K, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
+  if (rc) return rc;
+  cudaError_t e;
+  if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
+  else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
+  else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
+  else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
+  return e == cudaSuccess ? 0 : 1000 + int(e);
+}
+
+}  // namespace st

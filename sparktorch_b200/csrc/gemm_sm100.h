@@ -1,0 +1,33 @@
+// Host interface of the tcgen05 GEMM (see gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+struct GemmEpilogue {
+  float alpha = 1.f;
+  const float* bias = nullptr;            // [N] added per column
+  int relu = 0;
+  const __nv_bfloat16* mask_src = nullptr;  // [M, ld_mask]: keep D[m,n] only where mask_src[m,n] > 0
+  int64_t ld_mask = 0;
+  __nv_bfloat16* out_bf16 = nullptr;      // [M, ld_out] row-major
+  int64_t ld_out = 0;
+  __nv_bfloat16* out_t_bf16 = nullptr;    // [N, ld_out_t] transposed
+  int64_t ld_out_t = 0;
+  float* out_f32 = nullptr;               // [M, ld_f32]
+  int64_t ld_f32 = 0;
+  float* out_t_f32 = nullptr;             // [N, ld_f32_t]
+  int64_t ld_f32_t = 0;
+  int atomic_f32 = 0;                     // fp32 outputs use red.add (needed for split-K)
+  float* colsum = nullptr;                // [N] += sum_m D[m,n]
+};
+
+int gemm_pick_block_n(int N, int b_mn);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+              const GemmEpilogue* ep, int block_n, int split_k, cudaStream_t stream);
+
+}  // namespace st

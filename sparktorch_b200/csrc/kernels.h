@@ -1,0 +1,95 @@
+// Host-callable launchers of the non-GEMM kernels (raw pointers + stream).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+// ---- loss.cu
+int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,
+               __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
+               cudaStream_t stream);
+int mse_loss(const float* pred, int64_t ldp, const float* target, int64_t ldt, int B, int D, float* loss_slot,
+             __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
+             cudaStream_t stream);
+
+// ---- data.cu
+struct StepState {            // lives in device memory, advanced by the update kernel
+  uint32_t epoch;             // cross-GPU barrier epoch (monotonic)
+  uint32_t blocks_done;       // last-block detection
+  int64_t step;               // optimizer steps applied so far
+  int64_t iter;               // iterations launched so far (sampling / staging slot index)
+  uint32_t stopped;           // early stop latched
+  uint32_t es_seeded;
+  float es_best;
+  uint32_t es_bad;
+  float last_loss;
+  uint32_t pad[3];
+};
+
+struct GatherArgs {
+  const __nv_bfloat16* src;   // resident partition [n_rows, ld_src] or staging ring
+  int64_t ld_src;
+  int64_t n_rows;
+  const void* tgt_src;        // int32 labels [n_rows] or fp32 targets [n_rows, tgt_dim]
+  int tgt_dim;                // 0: int32 class labels
+  int mode;                   // 0 sequential window, 1 random w/o replacement (Feistel), 2 staging ring slot
+  int ring;                   // number of staging slots (mode 2)
+  uint64_t seed;
+  int B;
+  int D;
+  __nv_bfloat16* x;           // [B, ldx]
+  int64_t ldx;
+  __nv_bfloat16* xt;          // [D, ldxt]  (may be null)
+  int64_t ldxt;
+  void* tgt_out;              // int32 [B] or fp32 [B, tgt_dim]
+  const StepState* state;
+};
+int gather_batch(const GatherArgs& a, cudaStream_t stream);
+int transpose_bf16(const __nv_bfloat16* src, int64_t lds, int rows, int cols, __nv_bfloat16* dst, int64_t ldd, cudaStream_t stream);
+
+// ---- comm_ar.cu
+struct ParamSegment {         // one parameter tensor inside the flat arena
+  int64_t offset;             // first element in the flat fp32 arena
+  int32_t rows, cols;         // matrix view (bias: rows=1)
+  int64_t w_off;              // element offset of the bf16 copy in the bf16 arena (-1: none)
+  int32_t w_ld;
+  int64_t wt_off;             // element offset of the transposed bf16 copy (-1: none)
+  int32_t wt_ld;
+  int32_t publish_f32;        // 1: updated fp32 value is also stored to every peer's fp32 arena
+};
+
+struct UpdateArgs {
+  int world, rank;
+  // per-rank symmetric buffers (device pointers valid on THIS gpu; index = peer rank)
+  float* grad[8];             // gradient arena [total]
+  float* param[8];            // fp32 param arena [numel]
+  __nv_bfloat16* wbf16[8];    // bf16 weight arena
+  uint32_t* flags[8];         // signal pads [2][8][MAX_BLOCKS]
+  float* mc_grad;             // multicast (NVLS) alias of the gradient arena or null
+  float* m;                   // optimizer state (owned shard only is touched)
+  float* v;
+  StepState* state;
+  float* loss_hist;           // [max_iters] mean loss per iteration
+  int64_t max_iters;
+  volatile uint32_t* host_mailbox;  // pinned: [0]=stopped, [1]=iters done, [2]=as_float(last loss)
+  const ParamSegment* segs;
+  int n_segs;
+  int64_t numel;              // padded parameter elements (multiple of 64)
+  int tail;                   // piggy-back slots after numel
+  // optimizer
+  int kind;                   // 0 sgd, 1 adam, 2 adamw
+  float lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  int nesterov, maximize;
+  int patience;               // <=0: no early stopping
+  int zero_grads;             // zero the local gradient arena after the exchange
+};
+constexpr int AR_MAX_BLOCKS = 256;
+constexpr int AR_FLAG_WORDS = 2 * 8 * AR_MAX_BLOCKS;
+int allreduce_update(const UpdateArgs& a, cudaStream_t stream);
+int publish_params(const UpdateArgs& a, cudaStream_t stream);   // (re)build bf16 copies from fp32 master, no exchange
+int allreduce_sum_f32(float* const* bufs, uint32_t* const* flags, StepState* state, int world, int rank, int64_t n,
+                      int use_twoshot, cudaStream_t stream);
+
+}  // namespace st

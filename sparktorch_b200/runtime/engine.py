@@ -171,22 +171,28 @@ class DeviceSampler:
         return torch.randperm(self.n, device=self.device, generator=self.gen)[: self.batch]
 
 
-def build_comm(arena: FlatArena, spec: OptSpec, user_opt, cfg: TrainConfig, world: int, device: torch.device):
+def build_comm_and_arena(model: nn.Module, opt_cls, opt_params, cfg: TrainConfig, world: int, rank: int,
+                         device: torch.device):
+    """Pick the gradient-exchange back-end and lay the model out in its arena."""
     from sparktorch_b200.parallel.comm import CollectiveComm, LocalComm
 
+    spec = parse_optimizer(opt_cls, opt_params)
     patience = cfg.early_stop_patience
-    want_p2p = cfg.comm in ("auto", "p2p") and device.type == "cuda" and spec.kind != "other"
-    if want_p2p:
+    if cfg.comm in ("auto", "p2p") and device.type == "cuda" and spec.kind != "other":
         try:
             from sparktorch_b200.parallel.p2p import P2PFusedComm
 
-            return P2PFusedComm(arena, spec, patience=patience, world=world)
+            comm = P2PFusedComm(model, spec, patience, world, rank, device, cfg.iters)
+            return comm, comm.arena
         except Exception:
             if cfg.comm == "p2p":
                 raise
-    if world == 1:
-        return LocalComm(arena, spec, user_opt, patience)
-    return CollectiveComm(arena, spec, user_opt, patience)
+    arena = FlatArena(model, device)
+    user_opt = None
+    if spec.kind == "other":
+        user_opt = opt_cls(arena.params, **opt_params) if opt_params else opt_cls(arena.params)
+    comm = LocalComm(arena, spec, user_opt, patience) if world == 1 else CollectiveComm(arena, spec, user_opt, patience)
+    return comm, arena
 
 
 def train_partition(
@@ -254,12 +260,7 @@ def train_partition(
             model, criterion = swap_modules(model, criterion, precision=cfg.precision)
         except ImportError:
             pass
-    arena = FlatArena(model, device)
-    spec = parse_optimizer(opt_cls, opt_params)
-    user_opt = None
-    if spec.kind == "other":
-        user_opt = opt_cls(arena.params, **opt_params) if opt_params else opt_cls(arena.params)
-    comm = build_comm(arena, spec, user_opt, cfg, world, device)
+    comm, arena = build_comm_and_arena(model, opt_cls, opt_params, cfg, world, rank, device)
     comm.broadcast_params()
     step = EagerStep(model, criterion, arena)
 

@@ -27,6 +27,11 @@ def _round_up(x: int, m: int) -> int:
 
 
 class FlatArena:
+    @staticmethod
+    def measure(module: nn.Module) -> int:
+        """Padded number of fp32 elements the arena of ``module`` needs."""
+        return sum(_round_up(p.numel(), ALIGN) for p in module.parameters() if p.requires_grad)
+
     def __init__(self, module: nn.Module, device: torch.device, grad_buffer: torch.Tensor = None,
                  param_buffer: torch.Tensor = None):
         self.module = module

@@ -1,0 +1,491 @@
+"""Fused MLP training / inference on B200: no autograd, no Python in the loop.
+
+A model that lowers to ``Linear (+ReLU) ... Linear [+log_softmax]`` with
+CrossEntropy/NLL or MSE loss and Adam/AdamW/SGD becomes a static step plan of
+hand-written sm_100a kernels, captured once into a CUDA graph and replayed by
+the native ``GraphRunner``:
+
+    gather_batch                    device-side sampling of the step's rows
+    L x gemm_bf16 (fwd)             tcgen05 GEMM, bias(+ReLU) fused, bf16 out
+    softmax_ce | mse_loss           loss + dlogits + last bias grad, one pass
+    L x gemm_bf16 (wgrad)           dW = dZ^T A straight into the fp32 gradient arena
+                                    (both operands consumed MN-major: no transposes)
+    (L-1) x gemm_bf16 (dgrad)       dZ_prev = (dZ W) * (A>0), bias grad by column sums
+    allreduce_update (K-AR)         NVLink reduce-scatter + Adam/SGD + bf16 publish
+                                    + early-stop decision + loss history, one kernel
+
+This is the replacement of the reference hot loop (distributed.py:140-203) for
+its flagship workloads (examples/simple_dnn.py); anything that does not lower
+falls back to the eager engine.  bf16 tensor-core compute, fp32 master weights,
+fp32 optimizer state (ZeRO-1 sharded across the data-parallel ranks).
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+import time
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from sparktorch_b200.ops import native
+from sparktorch_b200.runtime.flat import TAIL, FlatArena
+from sparktorch_b200.runtime.optim import parse_optimizer
+
+
+def _pad(n: int, m: int = 8) -> int:
+    return (n + m - 1) // m * m
+
+
+@dataclasses.dataclass
+class LinearSpec:
+    module: nn.Linear
+    relu: bool
+
+
+@dataclasses.dataclass
+class Lowered:
+    layers: List[LinearSpec]
+    final_log_softmax: bool
+
+
+# ----------------------------------------------------------------------------- lowering
+def lower_mlp(model: nn.Module) -> Optional[Lowered]:
+    """FX-trace ``model`` and accept it iff it is a plain chain
+    Linear[,ReLU] ... Linear[,log_softmax] whose parameters are exactly the
+    Linear weights/biases."""
+    import torch.fx as fx
+
+    try:
+        gm = fx.symbolic_trace(model)
+    except Exception:
+        return None
+    mods = dict(gm.named_modules())
+    layers: List[LinearSpec] = []
+    final_lsm = False
+    prev = None
+    n_placeholder = 0
+    for node in gm.graph.nodes:
+        if node.op == "placeholder":
+            n_placeholder += 1
+            if n_placeholder > 1:
+                return None
+            prev = node
+            continue
+        if node.op == "output":
+            if node.args[0] is not prev:
+                return None
+            break
+        if final_lsm:
+            return None                       # nothing may follow the log_softmax
+        ins = [a for a in node.args if isinstance(a, fx.Node)]
+        if len(ins) != 1 or ins[0] is not prev or len(prev.users) != 1:
+            return None
+        if node.op == "call_module":
+            m = mods[node.target]
+            if isinstance(m, nn.Linear):
+                layers.append(LinearSpec(m, False))
+            elif isinstance(m, nn.ReLU):
+                if not layers or layers[-1].relu:
+                    return None
+                layers[-1].relu = True
+            elif isinstance(m, nn.LogSoftmax) and m.dim in (1, -1):
+                final_lsm = True
+            elif isinstance(m, (nn.Identity, nn.Flatten)):
+                pass
+            else:
+                return None
+        elif node.op == "call_function" and node.target in (F.relu, torch.relu):
+            if not layers or layers[-1].relu:
+                return None
+            layers[-1].relu = True
+        elif node.op == "call_method" and node.target == "relu":
+            if not layers or layers[-1].relu:
+                return None
+            layers[-1].relu = True
+        elif node.op == "call_function" and node.target in (F.log_softmax, torch.log_softmax):
+            dim = node.kwargs.get("dim", node.args[1] if len(node.args) > 1 else None)
+            if dim not in (1, -1):
+                return None
+            final_lsm = True
+        else:
+            return None
+        prev = node
+    if not layers or layers[-1].relu:
+        return None
+    covered = set()
+    for ls in layers:
+        covered.add(id(ls.module.weight))
+        if ls.module.bias is not None:
+            covered.add(id(ls.module.bias))
+    params = [p for p in model.parameters() if p.requires_grad]
+    if len(covered) != len(params) or any(id(p) not in covered for p in params):
+        return None
+    if len(list(model.buffers())) > 0:
+        return None
+    for a, b in zip(layers[:-1], layers[1:]):
+        if a.module.out_features != b.module.in_features:
+            return None
+    return Lowered(layers, final_lsm)
+
+
+def loss_kind(criterion, lowered: Lowered) -> Optional[str]:
+    if isinstance(criterion, nn.CrossEntropyLoss):
+        if criterion.weight is not None or criterion.reduction != "mean" or getattr(criterion, "label_smoothing", 0.0):
+            return None
+        return "ce"          # CE(log_softmax(z)) == CE(z): a trailing log_softmax is absorbed
+    if isinstance(criterion, nn.NLLLoss):
+        if not lowered.final_log_softmax or criterion.weight is not None or criterion.reduction != "mean":
+            return None
+        return "ce"
+    if isinstance(criterion, nn.MSELoss):
+        if criterion.reduction != "mean" or lowered.final_log_softmax:
+            return None
+        return "mse"
+    return None
+
+
+# ----------------------------------------------------------------------------- plan
+class FusedMLP:
+    """Device buffers + enqueue functions of one replica."""
+
+    def __init__(self, model: nn.Module, lowered: Lowered, kind: str, spec, world: int, rank: int,
+                 device: torch.device, batch: int, val_rows: int, patience: int, max_iters: int):
+        from sparktorch_b200.parallel.p2p import FusedUpdate
+
+        self.C = native.load(required=True)
+        self.device, self.world, self.rank = device, world, rank
+        self.kind, self.lowered = kind, lowered
+        self.B, self.nv = batch, val_rows
+        L = len(lowered.layers)
+        self.L = L
+        self.d = [lowered.layers[0].module.in_features] + [ls.module.out_features for ls in lowered.layers]
+        d = self.d
+        # ---- arenas (symmetric) -------------------------------------------------
+        numel = FlatArena.measure(model)
+        w_off, off = [], 0
+        for l in range(1, L + 1):
+            w_off.append(off)
+            off += _pad(d[l] * _pad(d[l - 1]), 64)
+        self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
+        self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
+        pos = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
+        rows, self.Wb, self.bias, self.gW, self.gb = [], [], [], [], []
+        seg_of = {}
+        for l, ls in enumerate(lowered.layers, start=1):
+            ldw = _pad(d[l - 1])
+            wo = pos[id(ls.module.weight)]
+            seg_of[wo] = [wo, d[l], d[l - 1], w_off[l - 1], ldw, -1, 0, 1]
+            self.Wb.append(self.fu.wbf16[w_off[l - 1]: w_off[l - 1] + d[l] * ldw].view(d[l], ldw)[:, : d[l - 1]])
+            self.gW.append(self.fu.grad[wo: wo + d[l] * d[l - 1]].view(d[l], d[l - 1]))
+            if ls.module.bias is not None:
+                bo = pos[id(ls.module.bias)]
+                seg_of[bo] = [bo, 1, d[l], -1, 0, -1, 0, 1]
+                self.bias.append(self.fu.param[bo: bo + d[l]])
+                self.gb.append(self.fu.grad[bo: bo + d[l]])
+            else:
+                self.bias.append(None)
+                self.gb.append(None)
+        for o in sorted(seg_of):
+            rows.append(seg_of[o])
+        self.fu.build(rows, zero_grads=True)
+        self.loss_slot = self.fu.grad[numel: numel + 1]          # tail[0]: rides in the all-reduce
+        self.train_loss_slot = self.fu.grad[numel + 2: numel + 3]  # tail[2]: local record when validating
+        # ---- activations ----------------------------------------------------------
+        self.train = self._alloc_acts(batch, backward=True)
+        self.val = self._alloc_acts(val_rows, backward=False) if val_rows > 0 else None
+        self.n_launch = 0
+
+    def _alloc_acts(self, rows: int, backward: bool):
+        d, L, dev = self.d, self.L, self.device
+        acts = [torch.zeros(rows, _pad(d[0]), dtype=torch.bfloat16, device=dev)[:, : d[0]]]
+        for l in range(1, L):
+            acts.append(torch.zeros(rows, _pad(d[l]), dtype=torch.bfloat16, device=dev)[:, : d[l]])
+        logits = torch.zeros(rows, _pad(d[L], 16), dtype=torch.float32, device=dev)[:, : d[L]]
+        dz = None
+        if backward:
+            dz = [None] + [torch.zeros(rows, _pad(d[l]), dtype=torch.bfloat16, device=dev)[:, : d[l]] for l in range(1, L + 1)]
+        if self.kind == "ce":
+            tgt = torch.zeros(rows, dtype=torch.int32, device=dev)
+        else:
+            tgt = torch.zeros(rows, d[L], dtype=torch.float32, device=dev)
+        return {"acts": acts, "logits": logits, "dz": dz, "tgt": tgt, "rows": rows}
+
+    # ---- enqueue helpers (everything goes to the current stream) -----------------
+    def _gemm(self, A, a_mn, Bm, b_mn, M, N, K, bias=None, relu=False, mask=None, out_bf16=None, out_f32=None,
+              atomic=False, colsum=None, split_k=1):
+        self.C.gemm_bf16(A, a_mn, Bm, b_mn, M, N, K, 1.0, bias, relu, mask, out_bf16, None, out_f32, None, atomic,
+                         colsum, 0, split_k)
+        self.n_launch += 1
+
+    def forward(self, buf) -> None:
+        acts, d, L, rows = buf["acts"], self.d, self.L, buf["rows"]
+        for l in range(1, L + 1):
+            last = l == L
+            self._gemm(acts[l - 1], False, self.Wb[l - 1], False, rows, d[l], d[l - 1], bias=self.bias[l - 1],
+                       relu=self.lowered.layers[l - 1].relu, out_bf16=None if last else acts[l],
+                       out_f32=buf["logits"] if last else None)
+
+    def loss(self, buf, slot, train: bool) -> None:
+        d, L = self.d, self.L
+        dz = buf["dz"][L] if train else None
+        db = self.gb[L - 1] if train else None
+        if self.kind == "ce":
+            self.C.softmax_ce(buf["logits"], buf["tgt"], d[L], slot, dz, None, db, _pad(d[L]))
+        else:
+            self.C.mse_loss(buf["logits"], buf["tgt"], d[L], slot, dz, None, db, _pad(d[L]))
+        self.n_launch += 1
+
+    def _split_k(self, M: int, N: int, K: int) -> int:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        kb = (K + 63) // 64
+        if kb < 8 or tiles >= 148:
+            return 1
+        return max(1, min(kb // 4, 148 // tiles))
+
+    def backward(self, buf) -> None:
+        acts, dz, d, L, rows = buf["acts"], buf["dz"], self.d, self.L, buf["rows"]
+        for l in range(L, 0, -1):
+            # wgrad: dW_l[d_l, d_{l-1}] = dZ_l^T A_{l-1}  (reduction over the batch; both operands MN-major)
+            sk = self._split_k(d[l], d[l - 1], rows)
+            self._gemm(dz[l], True, acts[l - 1], True, d[l], d[l - 1], rows, out_f32=self.gW[l - 1], atomic=sk > 1, split_k=sk)
+            if l > 1:
+                # dgrad: dZ_{l-1} = (dZ_l W_l) * (A_{l-1} > 0); db_{l-1} = column sums
+                relu_prev = self.lowered.layers[l - 2].relu
+                self._gemm(dz[l], False, self.Wb[l - 1], True, rows, d[l - 1], d[l], mask=acts[l - 1] if relu_prev else None,
+                           out_bf16=dz[l - 1], colsum=self.gb[l - 2])
+
+    def update(self) -> None:
+        self.fu.updater.step()
+        self.n_launch += 1
+
+    # ---- inference --------------------------------------------------------------------
+    def logits_of(self, x_bf16: torch.Tensor) -> torch.Tensor:
+        rows = x_bf16.shape[0]
+        buf = self._alloc_acts(rows, backward=False)
+        buf["acts"][0].copy_(x_bf16)
+        self.forward(buf)
+        return buf["logits"]
+
+
+# ----------------------------------------------------------------------------- training driver
+def _to_bf16_padded(x: torch.Tensor, device: torch.device, pin: bool = False) -> torch.Tensor:
+    """float [n, d] -> bf16 [n, pad8(d)] (zero padded); returns the [:, :d] view."""
+    n, d = x.shape
+    ld = _pad(d)
+    if pin:
+        out = torch.zeros(n, ld, dtype=torch.bfloat16).pin_memory()
+        out[:, :d].copy_(x)
+        return out[:, :d]
+    out = torch.zeros(n, ld, dtype=torch.bfloat16, device=device)
+    step = max(1, (64 << 20) // max(1, d * 4))
+    for s in range(0, n, step):
+        out[s: s + step, :d].copy_(x[s: s + step].to(device, non_blocking=True))
+    return out[:, :d]
+
+
+def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg, device, rng):
+    from sparktorch_b200.runtime.engine import FitResult, WindowTimer
+    from sparktorch_b200.util import split_validation
+
+    if cfg.precision not in ("auto", "bf16") or not native.available():
+        return None
+    spec = parse_optimizer(opt_cls, opt_params)
+    if spec.kind == "other" or world > 8:
+        return None
+    lowered = lower_mlp(model)
+    if lowered is None:
+        return None
+    kind = loss_kind(criterion, lowered)
+    if kind is None:
+        return None
+    d0, dL = lowered.layers[0].module.in_features, lowered.layers[-1].module.out_features
+    if X.shape[1] != d0:
+        return None
+    if kind == "mse":
+        if Y is None:
+            Y = X                                   # unsupervised: target = input
+        if Y.shape[1] != dL:
+            return None
+    elif Y is None:
+        return None
+    t_start = time.time()
+    torch.cuda.set_device(device)
+    C = native.load(required=True)
+
+    # ---- data --------------------------------------------------------------------------
+    xt = torch.from_numpy(np.ascontiguousarray(X))
+    yt = torch.from_numpy(np.ascontiguousarray(Y))
+    x_val = y_val = None
+    if cfg.validation_pct > 0:
+        tr, va = split_validation(X.shape[0], cfg.validation_pct, rng)
+        if len(va) > 0:
+            x_val, y_val = xt[torch.from_numpy(va)], yt[torch.from_numpy(va)]
+            xt, yt = xt[torch.from_numpy(tr)], yt[torch.from_numpy(tr)]
+    n = xt.shape[0]
+    use_mb = 0 < cfg.mini_batch < n
+    Bt = cfg.mini_batch if use_mb else n
+    streaming = bool(cfg.streaming and use_mb)
+    ytd = (yt.reshape(-1).to(torch.int32) if kind == "ce" else yt.to(torch.float32).reshape(n, -1))
+    nv = 0 if x_val is None else x_val.shape[0]
+
+    model = model.to(device)
+    plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.broadcast(plan.arena.flat_p, src=0)      # rank 0's weights win (quirk Q7)
+    stream = torch.cuda.Stream(device=device)
+    ring = 3
+    runner = C.GraphRunner()
+    seed = int(rng.integers(0, 2**62)) if cfg.seed is None else int(cfg.seed) * 1000003 + rank
+    with torch.cuda.stream(stream):
+        plan.fu.updater.publish()
+        if streaming:
+            x_host = _to_bf16_padded(xt, device, pin=True)
+            y_host = ytd.pin_memory()
+            xs = torch.zeros(ring * Bt, _pad(d0), dtype=torch.bfloat16, device=device)[:, :d0]
+            ys = torch.zeros((ring * Bt,) + tuple(ytd.shape[1:]), dtype=ytd.dtype, device=device)
+            src, tgt_src, n_src, mode = xs, ys, ring * Bt, 2
+        else:
+            src = _to_bf16_padded(xt, device)
+            tgt_src = ytd.to(device)
+            n_src, mode = n, (1 if os.environ.get("SPARKTORCH_SAMPLING", "random") == "random" else 0)
+        if nv:
+            plan.val["acts"][0].copy_(_to_bf16_padded(x_val, device))
+            plan.val["tgt"].copy_((y_val.reshape(-1).to(torch.int32) if kind == "ce" else y_val.to(torch.float32).reshape(nv, -1)).to(device))
+        if not use_mb:                               # full batch: the partition IS the batch
+            plan.train["acts"][0] = src
+            plan.train["tgt"] = tgt_src
+
+        def enqueue_step():
+            plan.n_launch = 0
+            if use_mb:
+                C.gather_batch(src, n_src, tgt_src, 0 if kind == "ce" else ytd.shape[1], mode, ring, seed, Bt, d0,
+                               plan.train["acts"][0], None, plan.train["tgt"], plan.fu.state)
+                plan.n_launch += 1
+            plan.forward(plan.train)
+            plan.loss(plan.train, plan.train_loss_slot if nv else plan.loss_slot, train=True)
+            plan.backward(plan.train)
+            if nv:
+                plan.forward(plan.val)
+                plan.loss(plan.val, plan.loss_slot, train=False)
+            plan.update()
+
+        # warm-up launch outside capture (module load, smem attributes), then rewind the step state
+        p0 = plan.fu.param.clone()
+        if streaming:
+            xs[:Bt].copy_(x_host[:Bt].to(device))
+            ys[:Bt].copy_(y_host[:Bt].to(device))
+        enqueue_step()
+        stream.synchronize()
+        plan.fu.param.copy_(p0)
+        for t in (plan.fu.m, plan.fu.v):
+            if t is not None:
+                t.zero_()
+        plan.fu.state[2:].zero_()                     # keep epoch/blocks_done, reset step/iter/early-stop record
+        plan.fu.loss_hist.zero_()
+        plan.fu.mailbox.zero_()
+        plan.fu.grad.zero_()
+        plan.fu.updater.publish()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        runner.begin_capture()
+        enqueue_step()
+        runner.end_capture()
+        launches = plan.n_launch
+        if streaming:
+            runner.setup_streaming(x_host.data_ptr(), y_host.data_ptr(), (n // Bt) * Bt, x_host.stride(0) * 2,
+                                   y_host.element_size() * (y_host[0].numel() if y_host.dim() > 1 else 1),
+                                   xs.data_ptr(), ys.data_ptr(), Bt, ring)
+
+        # ---- the loop: native, no Python per iteration ------------------------------------
+        window = WindowTimer(cfg.time_window, device, world)
+        mail_ptr = plan.fu.mailbox.data_ptr()
+        check = 1 if cfg.verbose else (4 if cfg.early_stop_patience > 0 else 0)
+        t_loop = time.time()
+        done = 0
+        segments = [(0, cfg.iters)]
+        if cfg.time_window is not None:
+            w0, wk = cfg.time_window
+            segments = [(0, w0), (w0, w0 + wk), (w0 + wk, cfg.iters)]
+        printed = 0
+        for seg_i, (lo, hi) in enumerate(segments):
+            if hi <= lo:
+                continue
+            timed = cfg.time_window is not None and seg_i == 1
+            if timed:
+                window.before_step(lo)
+            if cfg.verbose:
+                for i in range(lo, hi):
+                    got = runner.run(i, 1, mail_ptr, 1)
+                    stream.synchronize()
+                    done += got
+                    print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {plan.fu.last_loss()}")
+                    printed += 1
+                    if plan.fu.stopped():
+                        break
+            else:
+                done += runner.run(lo, hi - lo, mail_ptr, check)
+            if timed:
+                window.after_step(hi - 1)
+            if plan.fu.stopped():
+                break
+        stream.synchronize()
+    torch.cuda.synchronize(device)
+    t_end = time.time()
+    n_done = plan.fu.iters_done()
+    stopped = plan.fu.stopped()
+    losses = plan.fu.loss_hist[:n_done].cpu().tolist()
+    history = {
+        "engine": "fused_mlp", "comm": "P2PFused" + ("+NVLS" if plan.fu.use_multicast else ""), "precision": "bf16",
+        "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
+        "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
+        "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes(),
+        "streaming": streaming,
+        "h2d_bytes_per_step": (Bt * (_pad(d0) * 2 + (4 if kind == "ce" else 4 * dL))) if streaming else 0,
+        "d2h_bytes_per_step": 12,          # loss / iteration count / stop flag stored to the pinned mailbox every step
+    }
+    state = plan.arena.detach_state_dict() if rank == 0 else None
+    return FitResult(state, history)
+
+
+# ----------------------------------------------------------------------------- inference
+def try_fused_predictor(model: nn.Module, device: torch.device, precision: str = "auto") -> Optional[Callable]:
+    if precision not in ("auto", "bf16") or not native.available():
+        return None
+    lowered = lower_mlp(model)
+    if lowered is None:
+        return None
+    C = native.load(required=True)
+    d = [lowered.layers[0].module.in_features] + [ls.module.out_features for ls in lowered.layers]
+    Wb, bias = [], []
+    for l, ls in enumerate(lowered.layers, start=1):
+        w = torch.zeros(d[l], _pad(d[l - 1]), dtype=torch.bfloat16, device=device)
+        w[:, : d[l - 1]].copy_(ls.module.weight.detach())
+        Wb.append(w[:, : d[l - 1]])
+        bias.append(None if ls.module.bias is None else ls.module.bias.detach().float().contiguous())
+    L = len(lowered.layers)
+
+    def run(x: torch.Tensor) -> torch.Tensor:
+        rows = x.shape[0]
+        a = torch.zeros(rows, _pad(d[0]), dtype=torch.bfloat16, device=device)[:, : d[0]]
+        a.copy_(x)
+        for l in range(1, L + 1):
+            last = l == L
+            if last:
+                out = torch.zeros(rows, _pad(d[l], 16), dtype=torch.float32, device=device)[:, : d[l]]
+                C.gemm_bf16(a, False, Wb[l - 1], False, rows, d[l], d[l - 1], 1.0, bias[l - 1], False, None, None, None, out,
+                            None, False, None, 0, 1)
+                return torch.log_softmax(out, dim=1) if lowered.final_log_softmax else out
+            nxt = torch.zeros(rows, _pad(d[l]), dtype=torch.bfloat16, device=device)[:, : d[l]]
+            C.gemm_bf16(a, False, Wb[l - 1], False, rows, d[l], d[l - 1], 1.0, bias[l - 1], lowered.layers[l - 1].relu, None,
+                        nxt, None, None, None, False, None, 0, 1)
+            a = nxt
+        return a
+
+    return run

@@ -1,0 +1,158 @@
+"""End-to-end checks of the fused B200 path against the eager fp32 engine
+(``pytest -m gpu`` on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n=512, d=784, classes=10, seed=0):
+    rng = np.random.default_rng(seed)
+    X = (rng.integers(0, 256, size=(n, d)) * (rng.random((n, d)) < 0.2)).astype(np.float32) / 64.0
+    W = rng.normal(size=(d, classes)).astype(np.float32)
+    Y = (X @ W).argmax(1).astype(np.float32).reshape(n, 1)
+    return X, Y
+
+
+def _fit(model, crit, opt, kw, X, Y, **cfgkw):
+    from sparktorch_b200.runtime.engine import TrainConfig, train_partition
+
+    dev = torch.device("cuda", 0)
+    cfg = TrainConfig(device="cuda", seed=0, **cfgkw)
+    return train_partition(0, 1, model, crit, opt, kw, X, Y, cfg, dev)
+
+
+def test_lowering_accepts_and_rejects():
+    from sparktorch_b200.models import MnistCNN, mnist_dnn
+    from sparktorch_b200.runtime.fused_mlp import loss_kind, lower_mlp
+    from tests.nets import AutoEncoder, Classifier, Regressor
+
+    low = lower_mlp(mnist_dnn())
+    assert low is not None and [l.relu for l in low.layers] == [True, True, False]
+    assert lower_mlp(Regressor()) is not None and lower_mlp(AutoEncoder()) is not None
+    c = lower_mlp(Classifier())
+    assert c.final_log_softmax and loss_kind(nn.CrossEntropyLoss(), c) == "ce" and loss_kind(nn.NLLLoss(), c) == "ce"
+    assert loss_kind(nn.MSELoss(), c) is None
+    assert lower_mlp(MnistCNN()) is None
+    assert lower_mlp(nn.Sequential(nn.Linear(4, 4), nn.Tanh(), nn.Linear(4, 2))) is None
+    assert loss_kind(nn.CrossEntropyLoss(label_smoothing=0.1), low) is None
+
+
+def test_fused_mlp_tracks_eager_fp32_full_batch():
+    from sparktorch_b200.models import mnist_dnn
+
+    X, Y = _data()
+    torch.manual_seed(0)
+    net = mnist_dnn()
+    ref = _fit(__import__("copy").deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y,
+               iters=30, engine="eager", comm="collective", precision="fp32")
+    got = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=30, engine="fused")
+    assert got.history["engine"] == "fused_mlp" and ref.history["engine"] == "eager"
+    a, b = np.array(got.history["train_loss"]), np.array(ref.history["train_loss"])
+    assert len(a) == 30
+    np.testing.assert_allclose(a[0], b[0], rtol=2e-2)          # same init, same batch: bf16 rounding only
+    np.testing.assert_allclose(a, b, rtol=0.1, atol=0.02)
+    assert a[-1] < 0.7 * a[0]
+    for k in ref.state_dict:
+        torch.testing.assert_close(got.state_dict[k], ref.state_dict[k], rtol=0.2, atol=5e-3)
+
+
+def test_fused_mlp_minibatch_learns_and_counts_launches():
+    from sparktorch_b200.models import mnist_dnn
+
+    X, Y = _data(n=4096)
+    res = _fit(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=200, mini_batch=256, engine="fused")
+    h = res.history
+    assert h["engine"] == "fused_mlp" and h["iters_run"] == 200 and h["samples_per_step"] == 256
+    assert h["gpu_launches_per_step"] == 11 == h["graph_nodes"]     # gather + 3 fwd + loss + 3 wgrad + 2 dgrad + update
+    assert np.mean(h["train_loss"][-20:]) < 0.6 * np.mean(h["train_loss"][:5])
+
+
+def test_fused_mlp_mse_regression_and_sgd():
+    from tests.nets import Regressor
+
+    rng = np.random.default_rng(1)
+    X = rng.normal(size=(400, 10)).astype(np.float32)
+    Y = (X[:, :1] * 0.5 - X[:, 1:2]).astype(np.float32)
+    res = _fit(Regressor(), nn.MSELoss(), torch.optim.SGD, {"lr": 0.05, "momentum": 0.9}, X, Y, iters=150, engine="fused")
+    assert res.history["engine"] == "fused_mlp"
+    assert res.history["train_loss"][-1] < 0.1 * res.history["train_loss"][0]
+
+
+def test_fused_mlp_autoencoder_unsupervised():
+    from tests.nets import AutoEncoder
+
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(256, 10)).astype(np.float32)
+    res = _fit(AutoEncoder(), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, None, iters=50, engine="fused")
+    assert res.history["engine"] == "fused_mlp" and res.history["train_loss"][-1] < res.history["train_loss"][0]
+
+
+def test_fused_early_stop_in_band_and_validation():
+    from tests.nets import Regressor
+
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(300, 10)).astype(np.float32)
+    Y = rng.normal(size=(300, 1)).astype(np.float32)
+    res = _fit(Regressor(), nn.MSELoss(), torch.optim.SGD, {"lr": 0.0}, X, Y, iters=50, engine="fused", early_stop_patience=3)
+    assert res.history["stopped_at"] == 3 and res.history["iters_run"] == 4
+    res = _fit(Regressor(), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, Y, iters=30, engine="fused",
+               early_stop_patience=100, validation_pct=0.25, mini_batch=64)
+    assert res.history["iters_run"] == 30 and np.isfinite(res.history["train_loss"]).all()
+
+
+def test_streaming_from_pinned_host_matches_resident():
+    from sparktorch_b200.models import mnist_dnn
+    import os
+
+    X, Y = _data(n=2048)
+    os.environ["SPARKTORCH_SAMPLING"] = "sequential"
+    try:
+        torch.manual_seed(1)
+        net = mnist_dnn()
+        import copy
+
+        a = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, engine="fused")
+        b = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, engine="fused", streaming=True)
+    finally:
+        os.environ.pop("SPARKTORCH_SAMPLING")
+    assert b.history["streaming"] and b.history["h2d_bytes_per_step"] == 256 * (784 * 2 + 4)
+    np.testing.assert_allclose(a.history["train_loss"], b.history["train_loss"], rtol=1e-4, atol=1e-5)
+
+
+def test_eager_engine_uses_fused_update_kernel_on_gpu():
+    from sparktorch_b200.models import MnistCNN
+
+    rng = np.random.default_rng(4)
+    X = rng.random((256, 784)).astype(np.float32)
+    Y = rng.integers(0, 10, size=(256, 1)).astype(np.float32)
+    res = _fit(MnistCNN(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=12, mini_batch=64)
+    assert res.history["engine"] == "eager" and res.history["comm"] == "P2PFusedComm"
+    assert res.history["train_loss"][-1] < res.history["train_loss"][0] * 1.5 and np.isfinite(res.history["train_loss"]).all()
+
+
+def test_spark_api_on_gpu_and_batched_inference(tmp_path):
+    import sparktorch_b200  # noqa: F401
+    from pyspark.sql import SparkSession
+    from sparktorch_b200 import SparkTorch, serialize_torch_obj
+    from sparktorch_b200.models import mnist_dnn
+
+    spark = SparkSession.builder.master("local[1]").getOrCreate()
+    X, Y = _data(n=1024)
+    df = spark.createDataFrame({"label": Y.reshape(-1).astype(np.float64), "features": X}, numPartitions=1)
+    obj = serialize_torch_obj(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, lr=2e-3)
+    stm = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj, iters=150,
+                     miniBatch=256, device="cuda", seed=1).fit(df)
+    assert stm.getTrainingHistory()["engine"] == "fused_mlp"
+    rows = stm.transform(df).collect()
+    acc = np.mean([r["predictions"] == r["label"] for r in rows])
+    assert acc > 0.8
+    # fused predictor (bf16 tensor cores) agrees with the fp32 module
+    net = stm.getPytorchModel().cuda()
+    from sparktorch_b200.runtime.fused_mlp import try_fused_predictor
+
+    f = try_fused_predictor(net, torch.device("cuda", 0))
+    xb = torch.from_numpy(X[:300]).cuda()
+    torch.testing.assert_close(f(xb), net(xb), rtol=5e-2, atol=5e-2)
