@@ -162,7 +162,7 @@ def run_ours(args):
     def fit(streaming: bool):
         est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
                          iters=iters, verbose=0, mode="synchronous", device=args.device, miniBatch=args.batch,
-                         precision="bf16", engine=args.engine, seed=0, streaming=streaming)
+                         precision="bf16", engine=args.engine, seed=0, streaming=streaming, sampling="sweep")
         est._time_window = (args.warmup, args.steps)
         return est.fit(df).getTrainingHistory()
 
@@ -181,7 +181,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"model": "MNIST-DNN 784-256-256-10 CE Adam(lr=1e-3)", "global_batch": gb, "seq_len": IN_FEATURES,
                    "parallelism": f"dp{args.gpus}", "per_gpu_batch": args.batch, "mode": "synchronous",
-                   "engine": h.get("engine"), "comm": h.get("comm"),
+                   "engine": h.get("engine"), "comm": h.get("comm"), "sampling": h.get("sampling"),
                    "l2": f"inputs larger than L2: resident partition {rows}x{IN_FEATURES} per GPU "
                          f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
                          "weights/optimizer state stay cache resident as in any training loop"},

@@ -33,7 +33,8 @@ void req_2d(const Tensor& t, c10::ScalarType dt, const char* name) {
 void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M, int64_t N, int64_t K, double alpha,
                const OptT& bias, bool relu, const OptT& mask_src, const OptT& out_bf16, const OptT& out_t_bf16,
                const OptT& out_f32, const OptT& out_t_f32, bool atomic_f32, const OptT& colsum, int64_t block_n,
-               int64_t split_k) {
+               int64_t split_k, int64_t loss_kind, const OptT& labels, const OptT& target, const OptT& loss_slot,
+               double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
   c10::cuda::CUDAGuard guard(A.device());
@@ -48,8 +49,24 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
   if (out_f32) { req_2d(*out_f32, at::kFloat, "out_f32"); ep.out_f32 = out_f32->data_ptr<float>(); ep.ld_f32 = out_f32->stride(0); }
   if (out_t_f32) { req_2d(*out_t_f32, at::kFloat, "out_t_f32"); ep.out_t_f32 = out_t_f32->data_ptr<float>(); ep.ld_f32_t = out_t_f32->stride(0); }
   if (colsum) { TORCH_CHECK(colsum->scalar_type() == at::kFloat && colsum->numel() >= N); ep.colsum = colsum->data_ptr<float>(); }
+  ep.loss_kind = int(loss_kind);
+  if (loss_kind != 0) {
+    TORCH_CHECK(loss_slot.has_value() && loss_slot->scalar_type() == at::kFloat, "fused loss needs a float loss slot");
+    ep.loss_slot = loss_slot->data_ptr<float>();
+    ep.loss_scale = float(loss_scale);
+    if (loss_kind == 1) { TORCH_CHECK(labels.has_value() && labels->scalar_type() == at::kInt); ep.ce_labels = labels->data_ptr<int32_t>(); }
+    if (loss_kind == 2) { TORCH_CHECK(target.has_value()); req_2d(*target, at::kFloat, "target"); ep.mse_target = target->data_ptr<float>(); ep.ld_target = target->stride(0); }
+  }
+  st::GemmWindow win;
+  int64_t a_rows_total = 0, b_rows_total = 0;
+  if (win_state && win_flags != 0) {
+    win.state = reinterpret_cast<const st::StepState*>(win_state->data_ptr());
+    win.window_rows = window_rows; win.n_windows = n_windows > 0 ? n_windows : 1; win.flags = int(win_flags);
+    if (win_flags & 1) a_rows_total = A.size(0);
+    if (win_flags & 2) b_rows_total = B.size(0);
+  }
   check(st::gemm_bf16(A.data_ptr(), A.stride(0), a_mn ? 1 : 0, B.data_ptr(), B.stride(0), b_mn ? 1 : 0, int(M), int(N),
-                      int(K), &ep, int(block_n), int(split_k), cur_stream()),
+                      int(K), &ep, &win, a_rows_total, b_rows_total, int(block_n), int(split_k), cur_stream()),
         "gemm_bf16");
 }
 
@@ -251,6 +268,8 @@ class GraphRunner {
   uint64_t h2d_bytes_ = 0;
 };
 
+void set_pdl(bool on) { st::g_use_pdl = on; }
+bool get_pdl() { return st::g_use_pdl; }
 int64_t step_state_bytes() { return int64_t(sizeof(st::StepState)); }
 int64_t flag_words() { return st::AR_FLAG_WORDS; }
 
@@ -258,7 +277,14 @@ int64_t flag_words() { return st::AR_FLAG_WORDS; }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "sparktorch_b200 native kernels (sm_100a)";
-  m.def("gemm_bf16", &gemm_bf16, "tcgen05 bf16 GEMM with fused epilogue");
+  m.def("gemm_bf16", &gemm_bf16, "tcgen05 bf16 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"),
+        py::arg("b_mn"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("alpha") = 1.0, py::arg("bias") = py::none(),
+        py::arg("relu") = false, py::arg("mask_src") = py::none(), py::arg("out_bf16") = py::none(),
+        py::arg("out_t_bf16") = py::none(), py::arg("out_f32") = py::none(), py::arg("out_t_f32") = py::none(),
+        py::arg("atomic_f32") = false, py::arg("colsum") = py::none(), py::arg("block_n") = 0, py::arg("split_k") = 1,
+        py::arg("loss_kind") = 0, py::arg("labels") = py::none(), py::arg("target") = py::none(),
+        py::arg("loss_slot") = py::none(), py::arg("loss_scale") = 1.0, py::arg("win_state") = py::none(),
+        py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0);
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);
@@ -266,6 +292,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_sum", &allreduce_sum);
   m.def("pack_segments", &pack_segments);
   m.def("step_state_bytes", &step_state_bytes);
+  m.def("set_pdl", &set_pdl);
+  m.def("get_pdl", &get_pdl);
   m.def("flag_words", &flag_words);
   py::class_<Updater>(m, "Updater")
       .def(py::init<int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
     for (int i = threadIdx.x; i < a.n_segs; i += blockDim.x) s_segs[i] = a.segs[i];
     segs = s_segs;
   }
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     s_epoch = a.state->epoch + 1;
     s_stop = 0; s_stop_now = 0; s_loss = 0.f;
@@ -297,14 +299,12 @@ static int ar_grid(int64_t numel, int world) {
 
 int allreduce_update(const UpdateArgs& a, cudaStream_t stream) {
   if (a.world > 8 || (a.numel & 63)) return -1;
-  allreduce_update_kernel<0><<<ar_grid(a.numel, a.world), AR_THREADS, 0, stream>>>(a);
-  return int(cudaGetLastError());
+  return int(launch_kernel(allreduce_update_kernel<0>, dim3(ar_grid(a.numel, a.world)), dim3(AR_THREADS), 0, stream, a));
 }
 
 int publish_params(const UpdateArgs& a, cudaStream_t stream) {
   if (a.numel & 63) return -1;
-  allreduce_update_kernel<1><<<ar_grid(a.numel, 1), AR_THREADS, 0, stream>>>(a);
-  return int(cudaGetLastError());
+  return int(launch_kernel(allreduce_update_kernel<1>, dim3(ar_grid(a.numel, 1)), dim3(AR_THREADS), 0, stream, a));
 }
 
 // ----------------------------------------------------------------------------- plain all-reduce (bandwidth sweep, buffers)

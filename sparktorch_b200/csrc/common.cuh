@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 #define ST_DEVINL __device__ __forceinline__
 
@@ -23,6 +24,13 @@ ST_DEVINL bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// wait: block until the kernel(s) this launch programmatically depends on have completed and
+// their memory is visible (no-op for a normal launch).  launch_dependents: allow the next kernel
+// in the stream to start its prologue (barrier init, TMEM alloc, descriptor prefetch) now.
+ST_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+ST_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- mbarrier
 ST_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
@@ -164,6 +172,19 @@ ST_DEVINL void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32
 ST_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// host side: launch with (optional) programmatic stream serialization
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace st

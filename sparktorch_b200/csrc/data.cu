@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(GT_THREADS) gather_batch_kernel(const GatherAr
   __shared__ int64_t s_src_row[GT_ROWS];
   const int b0 = blockIdx.y * GT_ROWS;
   const int c0 = blockIdx.x * GT_COLS;
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t iter = a.state != nullptr ? a.state->iter : 0;
   if (threadIdx.x < GT_ROWS) {
     const int b = b0 + threadIdx.x;
@@ -105,8 +107,7 @@ __global__ void __launch_bounds__(GT_THREADS) gather_batch_kernel(const GatherAr
 int gather_batch(const GatherArgs& a, cudaStream_t stream) {
   const int64_t width = a.ldx > a.D ? a.ldx : a.D;
   dim3 grid(unsigned((width + GT_COLS - 1) / GT_COLS), unsigned((a.B + GT_ROWS - 1) / GT_ROWS));
-  gather_batch_kernel<<<grid, GT_THREADS, 0, stream>>>(a);
-  return int(cudaGetLastError());
+  return int(launch_kernel(gather_batch_kernel, grid, dim3(GT_THREADS), 0, stream, a));
 }
 
 __global__ void __launch_bounds__(GT_THREADS)

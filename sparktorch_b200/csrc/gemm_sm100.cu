@@ -19,8 +19,11 @@
 // bias/ReLU/threshold_backward/sum kernels for the same work.
 #include "common.cuh"
 #include "gemm_sm100.h"
+#include "kernels.h"
 
 namespace st {
+
+bool g_use_pdl = false;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
@@ -33,7 +36,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (STAGE_BYTES * 8 <= 200 * 1024) ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int BAR_BYTES = 1024;
+  static constexpr int BAR_BYTES = 2048;   // mbarriers + tmem slot (first 512 B), bias tile (up to 256 floats)
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
@@ -46,7 +49,7 @@ struct GemmSmem {
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmEpilogue ep, int M, int N, int K, int k_blocks_per_split) {
+                    const GemmEpilogue ep, const GemmWindow win, int M, int N, int K, int k_blocks_per_split) {
   using S = GemmSmem<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -54,6 +57,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tmem_full_bar = empty_bar + S::STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 512);   // [BLOCK_N] (BAR_BYTES = 2048)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -63,7 +67,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int kb_begin = blockIdx.z * k_blocks_per_split;
   const int kb_end = min(total_kb, kb_begin + k_blocks_per_split);
   const int num_kb = kb_end - kb_begin;   // >= 1 by construction of the grid
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -82,6 +85,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above touched only on-chip state and kernel parameters; from here on we read what
+  // earlier kernels of the step produced.
+  pdl_wait();
+  pdl_launch_dependents();
+  // Device-side mini-batch window: the batch of iteration i is rows [off, off + window_rows) of the
+  // resident partition; computed from the iteration counter the update kernel maintains, so the
+  // captured graph walks through the data without any host involvement or gather kernel.
+  int win_off = 0;
+  if (win.state != nullptr) win_off = int((win.state->iter % win.n_windows) * win.window_rows);
+  const int a_row_off = (win.flags & 1) ? win_off : 0;   // A K-major: outer (row) coordinate
+  const int b_k_off = (win.flags & 2) ? win_off : 0;     // B MN-major: K (row) coordinate
+  const int lbl_off = (win.flags & 4) ? win_off : 0;     // labels / targets of the fused loss
+
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -98,11 +114,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + 64 * j, k0);
         } else {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0 + a_row_off);
         }
         if constexpr (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + 64 * j, k0);
+          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + 64 * j, k0 + b_k_off);
         } else {
           tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
         }
@@ -138,9 +154,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;                    // TMEM lane quadrant this warp may read
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < M;
+    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
+    // Everything that does not depend on the accumulator is fetched while the main loop runs:
+    // the bias slice goes to shared memory, the first ReLU-mask chunk to registers.
+    const int et = threadIdx.x - 64;           // 0..127
+    if (ep.bias != nullptr) {
+      for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (n0 + c < N) ? ep.bias[n0 + c] : 0.f;
+    }
+    const bool have_mask = ep.mask_src != nullptr;
+    const __nv_bfloat16* mrow = have_mask ? ep.mask_src + size_t(row_ok ? row : 0) * ep.ld_mask : nullptr;
+    uint4 mk[4], mk_next[4];
+    auto load_mask = [&](uint4 (&dst)[4], int col0) {
+      if (have_mask && row_ok && col0 + CHUNK <= N) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mrow + col0);
+#pragma unroll
+        for (int v = 0; v < CHUNK / 8; ++v) dst[v] = mp[v];
+      }
+    };
+    load_mask(mk_next, n0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // s_bias visible to the four epilogue warps
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
       const int col0 = n0 + c0;
@@ -148,33 +182,68 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0);
       if constexpr (CHUNK == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
-      // overlap: fetch the mask tile row while the TMEM load is in flight
-      uint4 mk[4];
-      const bool full_chunk = (col0 + CHUNK <= N);
-      const bool vec_ok = full_chunk;          // leading dims are multiples of 8 elements, col0 multiple of 16
-      if (ep.mask_src != nullptr && row_ok && vec_ok) {
-        const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + size_t(row) * ep.ld_mask + col0);
+      const bool vec_ok = (col0 + CHUNK <= N);   // leading dims are multiples of 8 elements, col0 multiple of 16
 #pragma unroll
-        for (int v = 0; v < CHUNK / 8; ++v) mk[v] = mp[v];
-      }
+      for (int v = 0; v < 4; ++v) mk[v] = mk_next[v];
+      if (col0 + CHUNK < N) load_mask(mk_next, col0 + CHUNK);   // prefetch the next chunk's mask
       tmem_ld_wait();
       float acc[32];
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) {
         float v = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias != nullptr && col0 + j < N) v += ep.bias[col0 + j];
+        if (ep.bias != nullptr) v += s_bias[c0 + j];
         if (ep.relu) v = fmaxf(v, 0.f);
         acc[j] = v;
       }
-      if (ep.mask_src != nullptr) {
+      if (have_mask) {
         if (row_ok && vec_ok) {
           const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(mk);
 #pragma unroll
           for (int j = 0; j < CHUNK; ++j) acc[j] = (__bfloat162float(mb[j]) > 0.f) ? acc[j] : 0.f;
         } else if (row_ok) {
           for (int j = 0; j < CHUNK; ++j)
-            if (col0 + j < N) acc[j] = (__bfloat162float(ep.mask_src[size_t(row) * ep.ld_mask + col0 + j]) > 0.f) ? acc[j] : 0.f;
+            if (col0 + j < N) acc[j] = (__bfloat162float(mrow[col0 + j]) > 0.f) ? acc[j] : 0.f;
         }
+      }
+      // ---- row-major fp32 of the plain result (logits for inference / validation)
+      if (ep.out_f32 != nullptr && row_ok && ep.loss_kind != 0) {
+        float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
+        for (int j = 0; j < CHUNK; ++j)
+          if (col0 + j < N) op[j] = acc[j];
+      }
+      // ---- fused loss (single n-tile, N <= CHUNK): the thread owns the whole output row.
+      //      acc[] becomes dLoss/dOutput so the stores / column sums below emit dZ and db.
+      if (ep.loss_kind == 1) {          // softmax cross entropy, mean over M rows
+        const int y = row_ok ? ep.ce_labels[row + lbl_off] : 0;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) if (j < N) mx = fmaxf(mx, acc[j]);
+        float sum = 0.f, zy = 0.f;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          if (j == y) zy = acc[j];
+          acc[j] = (j < N) ? __expf(acc[j] - mx) : 0.f;
+          sum += acc[j];
+        }
+        float li = row_ok ? (mx + __logf(sum) - zy) : 0.f;
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) acc[j] = (row_ok && j < N) ? (acc[j] * inv - (j == y ? 1.f : 0.f)) * ep.loss_scale : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
+        if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
+      } else if (ep.loss_kind == 2) {   // mean squared error over M x N
+        float li = 0.f;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          float dlt = 0.f;
+          if (row_ok && j < N) dlt = acc[j] - ep.mse_target[size_t(row + lbl_off) * ep.ld_target + j];
+          li += dlt * dlt;
+          acc[j] = 2.f * dlt * ep.loss_scale;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
+        if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
       }
       if (!row_ok) {
 #pragma unroll
@@ -183,7 +252,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // ---- row-major bf16
       if (ep.out_bf16 != nullptr && row_ok) {
         __nv_bfloat16* op = ep.out_bf16 + size_t(row) * ep.ld_out + col0;
-        if (vec_ok) {
+        if (vec_ok || (col0 + CHUNK <= ep.ld_out && ep.loss_kind != 0)) {
+          // (fused loss: the padding columns up to the pitch are written as zeros)
 #pragma unroll
           for (int v = 0; v < CHUNK / 8; ++v) {
             uint4 w;
@@ -191,7 +261,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
             w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]);
             w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
-            reinterpret_cast<uint4*>(op)[v] = w;
+            if (col0 + 8 * v < ep.ld_out) reinterpret_cast<uint4*>(op)[v] = w;
           }
         } else {
           for (int j = 0; j < CHUNK; ++j)
@@ -199,7 +269,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       // ---- row-major fp32 (store or red.add for split-K)
-      if (ep.out_f32 != nullptr && row_ok) {
+      if (ep.out_f32 != nullptr && row_ok && ep.loss_kind == 0) {
         float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
         if (ep.atomic_f32) {
           for (int j = 0; j < CHUNK; ++j)
@@ -289,18 +359,21 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
-int gemm_pick_block_n(int N, int b_mn) {
-  if (!b_mn) {
-    if (N <= 16) return 16;
-    if (N <= 32) return 32;
-  }
-  if (N <= 64) return 64;
-  return 128;
+// Tile width: the smallest power of two covering N, then shrunk further until ~64 CTAs are in
+// flight (tiny problems are bound by how much ONE SM can pull from L2, so they want many small
+// tiles); big problems keep 128-wide tiles.
+int gemm_pick_block_n(int M, int N, int b_mn) {
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int min_bn = b_mn ? 64 : 16;
+  int bn = 128;
+  while (bn > min_bn && bn / 2 >= N) bn >>= 1;
+  while (bn > min_bn && tiles_m * ((N + bn - 1) / bn) < 64) bn >>= 1;
+  return bn;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                             int split_k, cudaStream_t stream) {
+static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, const GemmWindow& win,
+                             int M, int N, int K, int split_k, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -312,19 +385,18 @@ static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const
   int kb_per = (total_kb + split_k - 1) / split_k;
   int splits = (total_kb + kb_per - 1) / kb_per;      // no empty splits
   dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, splits);
-  gemm_bf16_tn_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, ep, M, N, K, kb_per);
-  return cudaGetLastError();
+  return launch_kernel(gemm_bf16_tn_kernel<BN, A_MN, B_MN>, grid, dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, ep, win, M, N, K, kb_per);
 }
 
 template <bool A_MN, bool B_MN>
-static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
-                               int N, int K, int split_k, cudaStream_t stream) {
+static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
+                               const GemmWindow& win, int M, int N, int K, int split_k, cudaStream_t stream) {
   switch (block_n) {
-    case 16: if constexpr (!B_MN) return launch_bn<16, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream); break;
-    case 32: if constexpr (!B_MN) return launch_bn<32, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream); break;
-    case 64: return launch_bn<64, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
-    case 128: return launch_bn<128, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
-    case 256: return launch_bn<256, A_MN, B_MN>(ta, tb, ep, M, N, K, split_k, stream);
+    case 16: if constexpr (!B_MN) return launch_bn<16, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream); break;
+    case 32: if constexpr (!B_MN) return launch_bn<32, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream); break;
+    case 64: return launch_bn<64, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
+    case 128: return launch_bn<128, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
+    case 256: return launch_bn<256, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -332,23 +404,30 @@ static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtenso
 // D[M,N] = A * B^T.  a_mn=0: A stored [M,K] (pitch lda); a_mn=1: A stored [K,M].  Same for B with N.
 // bf16, base pointers 16-byte aligned, pitches multiples of 8 elements.
 int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
-              const GemmEpilogue* ep, int block_n, int split_k, cudaStream_t stream) {
+              const GemmEpilogue* ep, const GemmWindow* winp, int64_t a_rows_total, int64_t b_rows_total, int block_n,
+              int split_k, cudaStream_t stream) {
+  GemmWindow win{};
+  if (winp != nullptr) win = *winp;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -2;
-  if (block_n <= 0) block_n = gemm_pick_block_n(N, b_mn);
+  if (block_n <= 0) block_n = gemm_pick_block_n(M, N, b_mn);
+  if (ep->loss_kind != 0 && N > (block_n >= 32 ? 32 : 16)) return -5;   // fused loss needs the row in one chunk
   if (b_mn && block_n < 64) block_n = 64;
   if (split_k <= 0) split_k = 1;
   if (split_k > 1 && !ep->atomic_f32) return -3;
   CUtensorMap ta, tb;
-  int rc = a_mn ? make_tmap_bf16_2d(&ta, A, K, M, lda, BLOCK_K) : make_tmap_bf16_2d(&ta, A, M, K, lda, BLOCK_M);
+  // windowed operands are described over the whole resident matrix (rows_total), the kernel adds the offset
+  const uint64_t a_rows = (win.flags & 1) && a_rows_total > 0 ? uint64_t(a_rows_total) : uint64_t(M);
+  const uint64_t b_krows = (win.flags & 2) && b_rows_total > 0 ? uint64_t(b_rows_total) : uint64_t(K);
+  int rc = a_mn ? make_tmap_bf16_2d(&ta, A, K, M, lda, BLOCK_K) : make_tmap_bf16_2d(&ta, A, a_rows, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = b_mn ? make_tmap_bf16_2d(&tb, B, K, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
+  rc = b_mn ? make_tmap_bf16_2d(&tb, B, b_krows, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
   if (rc) return rc;
   cudaError_t e;
-  if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
-  else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
-  else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
-  else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, M, N, K, split_k, stream);
+  if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
+  else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
+  else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
+  else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
   return e == cudaSuccess ? 0 : 1000 + int(e);
 }
 

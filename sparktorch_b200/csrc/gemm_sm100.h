@@ -23,11 +23,30 @@ struct GemmEpilogue {
   int64_t ld_f32_t = 0;
   int atomic_f32 = 0;                     // fp32 outputs use red.add (needed for split-K)
   float* colsum = nullptr;                // [N] += sum_m D[m,n]
+  // fused loss on the output row (needs N <= 32, one n-tile): 0 none, 1 softmax-CE, 2 MSE.
+  // acc becomes dLoss/dOut, so out_bf16 / colsum then emit dZ / db; out_f32 (if set) keeps the raw output.
+  int loss_kind = 0;
+  const int32_t* ce_labels = nullptr;     // [rows] class index
+  const float* mse_target = nullptr;      // [rows, ld_target]
+  int64_t ld_target = 0;
+  float* loss_slot = nullptr;             // += loss * loss_scale
+  float loss_scale = 1.f;                 // 1/M (CE) or 1/(M*N) (MSE)
 };
 
-int gemm_pick_block_n(int N, int b_mn);
+struct StepState;                         // kernels.h
+
+// Mini-batch window taken on the device from StepState::iter (no gather kernel, no host in the loop).
+struct GemmWindow {
+  const StepState* state = nullptr;
+  int64_t window_rows = 0;
+  int64_t n_windows = 1;
+  int flags = 0;                          // 1: offset A rows (K-major A), 2: offset B's K rows (MN-major B), 4: offset labels/targets
+};
+
+int gemm_pick_block_n(int M, int N, int b_mn);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
-              const GemmEpilogue* ep, int block_n, int split_k, cudaStream_t stream);
+              const GemmEpilogue* ep, const GemmWindow* win, int64_t a_rows_total, int64_t b_rows_total, int block_n,
+              int split_k, cudaStream_t stream);
 
 }  // namespace st

@@ -6,6 +6,8 @@
 
 namespace st {
 
+extern bool g_use_pdl;   // launch the step kernels with programmatic dependent launch
+
 // ---- loss.cu
 int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,
                __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,

@@ -22,6 +22,8 @@ softmax_ce_kernel(const float* __restrict__ logits, int64_t ldz, const int32_t* 
   __shared__ float s_db[MAX_SMEM_CLASSES];
   __shared__ float s_loss;
   const bool want_db = db != nullptr && C <= MAX_SMEM_CLASSES;
+  pdl_wait();
+  pdl_launch_dependents();
   for (int c = threadIdx.x; c < C && want_db; c += blockDim.x) s_db[c] = 0.f;
   if (threadIdx.x == 0) s_loss = 0.f;
   __syncthreads();
@@ -73,6 +75,8 @@ mse_kernel(const float* __restrict__ pred, int64_t ldp, const float* __restrict_
   __shared__ float s_db[MAX_SMEM_CLASSES];
   __shared__ float s_loss;
   const bool want_db = db != nullptr && D <= MAX_SMEM_CLASSES;
+  pdl_wait();
+  pdl_launch_dependents();
   for (int c = threadIdx.x; c < D && want_db; c += blockDim.x) s_db[c] = 0.f;
   if (threadIdx.x == 0) s_loss = 0.f;
   __syncthreads();
@@ -113,17 +117,15 @@ static int grid_for(int64_t work_items, int per_block) {
 int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,
                __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
                cudaStream_t stream) {
-  softmax_ce_kernel<<<grid_for(B, LOSS_THREADS / 32), LOSS_THREADS, 0, stream>>>(logits, ldz, labels, B, C, loss_slot, dz,
-                                                                                 ld_dz, dzt, ld_dzt, db, pad_cols);
-  return int(cudaGetLastError());
+  return int(launch_kernel(softmax_ce_kernel, dim3(grid_for(B, LOSS_THREADS / 32)), dim3(LOSS_THREADS), 0, stream, logits, ldz,
+                           labels, B, C, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols));
 }
 
 int mse_loss(const float* pred, int64_t ldp, const float* target, int64_t ldt, int B, int D, float* loss_slot,
              __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
              cudaStream_t stream) {
-  mse_kernel<<<grid_for(int64_t(B) * pad_cols, LOSS_THREADS), LOSS_THREADS, 0, stream>>>(pred, ldp, target, ldt, B, D, loss_slot,
-                                                                                       dz, ld_dz, dzt, ld_dzt, db, pad_cols);
-  return int(cudaGetLastError());
+  return int(launch_kernel(mse_kernel, dim3(grid_for(int64_t(B) * pad_cols, LOSS_THREADS)), dim3(LOSS_THREADS), 0, stream, pred,
+                           ldp, target, ldt, B, D, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols));
 }
 
 }  // namespace st

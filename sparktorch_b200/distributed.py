@@ -47,6 +47,7 @@ def handle_model(
     seed: int = None,
     streaming: bool = False,
     time_window=None,
+    sampling: str = "random",
 ) -> List[Dict]:
     """Body of one barrier task = one replica (reference distributed.py:66-205).
 
@@ -69,7 +70,7 @@ def handle_model(
             iters=iters, mini_batch=mini_batch, validation_pct=validation_pct,
             early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev),
             precision=precision, engine=engine, comm=comm, seed=seed, streaming=streaming,
-            time_window=tuple(time_window) if time_window else None,
+            time_window=tuple(time_window) if time_window else None, sampling=sampling,
         )
         res = train_partition(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y, cfg, dev)
     finally:
@@ -97,6 +98,7 @@ def train_distributed(
     streaming: bool = False,
     return_history: bool = False,
     time_window=None,
+    sampling: str = "random",
 ):
     """Driver entry: run the barrier stage ``partition_shuffles`` times,
     reshuffling partitions in between and carrying the weights over (the
@@ -112,7 +114,7 @@ def train_distributed(
                 validation_pct=validation_pct, device=device,
                 early_stop_patience=int(early_stop_patience), compile_mode=compile_mode,
                 precision=precision, engine=engine, comm=comm, seed=seed, streaming=streaming,
-                time_window=time_window,
+                time_window=time_window, sampling=sampling,
             )
 
         task._accepts_blocks = True

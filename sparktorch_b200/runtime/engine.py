@@ -50,6 +50,7 @@ class TrainConfig:
     seed: Optional[int] = None
     streaming: bool = False       # keep the partition in pinned host memory, H2D one batch per step
     time_window: Optional[Tuple[int, int]] = None   # (first_step, n_steps): device-time this window (bench/profiling)
+    sampling: str = "random"      # random: fresh sample w/o replacement per step | sweep: walk the shuffled partition
 
 
 @dataclasses.dataclass

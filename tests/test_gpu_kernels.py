@@ -114,6 +114,77 @@ def test_gemm_wgrad_split_k_atomic(C):
     torch.testing.assert_close(dw2, dz.float().t() @ a.float(), rtol=2e-3, atol=5e-2)
 
 
+def test_gemm_fused_ce_epilogue(C):
+    # logits = a W^T + b, then softmax-CE in the SAME kernel: loss, dZ (bf16, zero padded), db
+    Bt, I, Cn = 300, 256, 10
+    a, w = _mk(Bt, I, 0.2, 40), _mk(Cn, I, 0.2, 41)
+    b = torch.randn(Cn, device=dev())
+    y = torch.randint(0, Cn, (Bt,), device=dev(), dtype=torch.int32)
+    loss = torch.zeros(1, device=dev())
+    dz = torch.full((Bt, 16), 7.0, dtype=torch.bfloat16, device=dev())[:, :Cn]
+    db = torch.zeros(Cn, device=dev())
+    logits = torch.zeros(Bt, 16, device=dev())[:, :Cn]
+    C.gemm_bf16(a, False, w, False, Bt, Cn, I, bias=b, out_bf16=dz, colsum=db, out_f32=logits, loss_kind=1, labels=y,
+                loss_slot=loss, loss_scale=1.0 / Bt)
+    zr = (a.float() @ w.float().t() + b).requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(zr, y.long())
+    ref.backward()
+    torch.testing.assert_close(logits, zr.detach(), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dz.float(), zr.grad, rtol=2e-2, atol=1e-5)
+    full = dz.as_strided((Bt, 16), (16, 1))
+    assert full[:, Cn:].abs().max().item() == 0
+    torch.testing.assert_close(db, zr.grad.sum(0), rtol=1e-2, atol=1e-4)
+    # loss-only (validation) mode
+    l2 = torch.zeros(1, device=dev())
+    C.gemm_bf16(a, False, w, False, Bt, Cn, I, bias=b, loss_kind=1, labels=y, loss_slot=l2, loss_scale=1.0 / Bt)
+    torch.testing.assert_close(l2[0], ref.detach(), rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_fused_mse_epilogue(C):
+    Bt, I, D = 200, 20, 3
+    a, w = _mk(Bt, I, 0.5, 42), _mk(D, I, 0.5, 43)
+    t = torch.randn(Bt, D, device=dev())
+    loss = torch.zeros(1, device=dev())
+    dz = torch.zeros(Bt, 8, dtype=torch.bfloat16, device=dev())[:, :D]
+    db = torch.zeros(D, device=dev())
+    C.gemm_bf16(a, False, w, False, Bt, D, I, out_bf16=dz, colsum=db, loss_kind=2, target=t, loss_slot=loss,
+                loss_scale=1.0 / (Bt * D))
+    pr = (a.float() @ w.float().t()).requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(pr, t)
+    ref.backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dz.float(), pr.grad, rtol=2e-2, atol=1e-5)
+    torch.testing.assert_close(db, pr.grad.sum(0), rtol=1e-2, atol=1e-4)
+
+
+def test_gemm_device_side_batch_windows(C):
+    # the batch is window (iter % n_windows) of a resident partition, selected inside the kernel
+    n, Bt, I, O, Cn = 1024, 256, 784, 256, 10
+    X = _mk(n, I, 0.1, 44)
+    w = _mk(O, I, 0.1, 45)
+    state = torch.zeros(C.step_state_bytes() // 4, dtype=torch.int32, device=dev())
+    for it in (0, 3, 6):
+        state.view(torch.int64)[2] = it
+        off = (it % (n // Bt)) * Bt
+        y = torch.zeros(Bt, O, dtype=torch.bfloat16, device=dev())
+        C.gemm_bf16(X, False, w, False, Bt, O, I, out_bf16=y, win_state=state, window_rows=Bt, n_windows=n // Bt, win_flags=1)
+        torch.testing.assert_close(y.float(), X[off:off + Bt].float() @ w.float().t(), rtol=2e-2, atol=2e-2)
+        # wgrad with the windowed partition as MN-major B operand: dW = dz^T X[window]
+        dzz = _mk(Bt, O, 0.05, 46)
+        dw = torch.zeros(O, I, device=dev())
+        C.gemm_bf16(dzz, True, X, True, O, I, Bt, out_f32=dw, win_state=state, window_rows=Bt, n_windows=n // Bt, win_flags=2)
+        torch.testing.assert_close(dw, dzz.float().t() @ X[off:off + Bt].float(), rtol=2e-3, atol=2e-2)
+        # windowed labels for the fused loss
+        labels = torch.randint(0, Cn, (n,), device=dev(), dtype=torch.int32)
+        a, wc = _mk(Bt, O, 0.2, 47), _mk(Cn, O, 0.2, 48)
+        loss = torch.zeros(1, device=dev())
+        C.gemm_bf16(a, False, wc, False, Bt, Cn, O, loss_kind=1, labels=labels, loss_slot=loss, loss_scale=1.0 / Bt,
+                    win_state=state, window_rows=Bt, n_windows=n // Bt, win_flags=4)
+        ref = torch.nn.functional.cross_entropy(a.float() @ wc.float().t(), labels[off:off + Bt].long())
+        torch.testing.assert_close(loss[0], ref, rtol=1e-4, atol=1e-4)
+
+
 def test_softmax_ce_kernel(C):
     Bt, Cn = 300, 10
     z = torch.randn(Bt, 16, device=dev())[:, :Cn] * 3
