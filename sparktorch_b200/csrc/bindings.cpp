@@ -34,7 +34,8 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
                const OptT& bias, bool relu, const OptT& mask_src, const OptT& out_bf16, const OptT& out_t_bf16,
                const OptT& out_f32, const OptT& out_t_f32, bool atomic_f32, const OptT& colsum, int64_t block_n,
                int64_t split_k, int64_t loss_kind, const OptT& labels, const OptT& target, const OptT& loss_slot,
-               double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags) {
+               double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags,
+               const OptT& prof) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
   c10::cuda::CUDAGuard guard(A.device());
@@ -57,6 +58,7 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
     if (loss_kind == 1) { TORCH_CHECK(labels.has_value() && labels->scalar_type() == at::kInt); ep.ce_labels = labels->data_ptr<int32_t>(); }
     if (loss_kind == 2) { TORCH_CHECK(target.has_value()); req_2d(*target, at::kFloat, "target"); ep.mse_target = target->data_ptr<float>(); ep.ld_target = target->stride(0); }
   }
+  if (prof) { TORCH_CHECK(prof->scalar_type() == at::kLong); ep.prof = reinterpret_cast<long long*>(prof->data_ptr()); }
   st::GemmWindow win;
   int64_t a_rows_total = 0, b_rows_total = 0;
   if (win_state && win_flags != 0) {
@@ -171,6 +173,41 @@ void allreduce_sum(std::vector<int64_t> buf_ptrs, std::vector<int64_t> flag_ptrs
         "allreduce_sum");
 }
 
+// ------------------------------------------------------------------ hogwild over peer memory
+class HogwildWorker {
+ public:
+  HogwildWorker(int64_t world, int64_t rank, int64_t stripes, std::vector<int64_t> param_ptrs, std::vector<int64_t> m_ptrs,
+                std::vector<int64_t> v_ptrs, std::vector<int64_t> ctrl_ptrs, const Tensor& local_param, const Tensor& local_grad,
+                const Tensor& loss_in, bool use_val_loss, int64_t numel, bool acquire_lock, int64_t kind, double lr, double beta1,
+                double beta2, double eps, double weight_decay, double momentum, double dampening, bool nesterov, bool maximize,
+                int64_t patience, int64_t window_len, int64_t host_mailbox_ptr)
+      : lp_(local_param), lg_(local_grad), li_(loss_in) {
+    a_ = st::HogwildArgs{};
+    a_.world = int(world); a_.rank = int(rank); a_.stripes = int(stripes);
+    for (int r = 0; r < world; ++r) {
+      a_.param[r] = reinterpret_cast<float*>(param_ptrs[r]);
+      a_.m[r] = m_ptrs.empty() ? nullptr : reinterpret_cast<float*>(m_ptrs[r]);
+      a_.v[r] = v_ptrs.empty() ? nullptr : reinterpret_cast<float*>(v_ptrs[r]);
+      a_.ctrl[r] = reinterpret_cast<uint32_t*>(ctrl_ptrs[r]);
+    }
+    a_.local_param = local_param.data_ptr<float>(); a_.local_grad = local_grad.data_ptr<float>();
+    a_.loss_in = loss_in.data_ptr<float>(); a_.use_val_loss = use_val_loss;
+    a_.numel = numel; a_.acquire_lock = acquire_lock; a_.kind = int(kind);
+    a_.lr = float(lr); a_.beta1 = float(beta1); a_.beta2 = float(beta2); a_.eps = float(eps);
+    a_.weight_decay = float(weight_decay); a_.momentum = float(momentum); a_.dampening = float(dampening);
+    a_.nesterov = nesterov; a_.maximize = maximize; a_.patience = int(patience); a_.window_len = int(window_len);
+    a_.host_mailbox = reinterpret_cast<volatile uint32_t*>(host_mailbox_ptr);
+  }
+  void pull() { check(st::hogwild_pull(a_, cur_stream()), "hogwild_pull"); }
+  void push() { check(st::hogwild_push(a_, cur_stream()), "hogwild_push"); }
+
+ private:
+  st::HogwildArgs a_;
+  Tensor lp_, lg_, li_;
+};
+int64_t hw_ctrl_words() { return st::HW_CTRL_WORDS; }
+int64_t hw_max_stripes() { return st::HW_MAX_STRIPES; }
+
 py::bytes pack_segments(const std::vector<std::vector<int64_t>>& rows) {
   std::vector<st::ParamSegment> segs(rows.size());
   for (size_t i = 0; i < rows.size(); ++i) {
@@ -284,7 +321,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("atomic_f32") = false, py::arg("colsum") = py::none(), py::arg("block_n") = 0, py::arg("split_k") = 1,
         py::arg("loss_kind") = 0, py::arg("labels") = py::none(), py::arg("target") = py::none(),
         py::arg("loss_slot") = py::none(), py::arg("loss_scale") = 1.0, py::arg("win_state") = py::none(),
-        py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0);
+        py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0,
+        py::arg("prof") = py::none());
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);
@@ -302,6 +340,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("step", &Updater::step)
       .def("publish", &Updater::publish)
       .def("set_lr", &Updater::set_lr);
+  m.def("hw_ctrl_words", &hw_ctrl_words);
+  m.def("hw_max_stripes", &hw_max_stripes);
+  py::class_<HogwildWorker>(m, "HogwildWorker")
+      .def(py::init<int64_t, int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,
+                    std::vector<int64_t>, const Tensor&, const Tensor&, const Tensor&, bool, int64_t, bool, int64_t, double,
+                    double, double, double, double, double, double, bool, bool, int64_t, int64_t, int64_t>())
+      .def("pull", &HogwildWorker::pull)
+      .def("push", &HogwildWorker::push);
   py::class_<GraphRunner>(m, "GraphRunner")
       .def(py::init<>())
       .def("begin_capture", &GraphRunner::begin_capture)

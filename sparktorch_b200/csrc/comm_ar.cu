@@ -158,12 +158,21 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
     hi4 = lo4 + per < n4 ? lo4 + per : n4;
     if (lo4 > n4) lo4 = n4;
   }
-  OptConsts oc{1.f, 1.f};
-  const int64_t step1 = a.state->step + 1;   // 1-based step being applied
-  if (a.kind != 0) {
-    oc.bc1_inv = 1.f / (1.f - powf(a.beta1, float(step1)));
-    oc.bc2_inv_sqrt = rsqrtf(1.f - powf(a.beta2, float(step1)));
+  __shared__ OptConsts s_oc;
+  __shared__ long long s_step1;
+  if (threadIdx.x == 32 || (blockDim.x <= 32 && threadIdx.x == 0)) {   // one thread per block pays for the powf
+    const int64_t st1 = a.state->step + 1;                             // 1-based step being applied
+    s_step1 = st1;
+    OptConsts t{1.f, 1.f};
+    if (a.kind != 0) {
+      t.bc1_inv = 1.f / (1.f - powf(a.beta1, float(st1)));
+      t.bc2_inv_sqrt = rsqrtf(1.f - powf(a.beta2, float(st1)));
+    }
+    s_oc = t;
   }
+  __syncthreads();
+  const OptConsts oc = s_oc;
+  const int64_t step1 = s_step1;
   const float inv_w = 1.f / float(W);
   const int n_pub = (MODE == 0) ? W : 1;
 
@@ -284,7 +293,6 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
         }
       }
     }
-    __threadfence_system();
   }
 }
 

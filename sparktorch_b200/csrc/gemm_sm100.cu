@@ -61,6 +61,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* prof = ep.prof ? ep.prof + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (prof && threadIdx.x == 0) prof[0] = clock64();
   const int m0 = blockIdx.y * BLOCK_M;
   const int n0 = blockIdx.x * BLOCK_N;
   const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -85,10 +87,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (prof && threadIdx.x == 0) prof[1] = clock64();
   // Everything above touched only on-chip state and kernel parameters; from here on we read what
   // earlier kernels of the step produced.
   pdl_wait();
   pdl_launch_dependents();
+  if (prof && threadIdx.x == 0) prof[2] = clock64();
   // Device-side mini-batch window: the batch of iteration i is rows [off, off + window_rows) of the
   // resident partition; computed from the iteration counter the update kernel maintains, so the
   // captured graph walks through the data without any host involvement or gather kernel.
@@ -133,6 +137,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t ph = (i / S::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (prof && i == 0) prof[3] = clock64();
         const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t sb = sa + S::A_BYTES;
         const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
@@ -175,6 +180,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("bar.sync 1, 128;" ::: "memory");   // s_bias visible to the four epilogue warps
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (prof && et == 0) prof[4] = clock64();
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
       const int col0 = n0 + c0;
@@ -322,10 +328,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) prof[5] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
+  if (prof && threadIdx.x == 32) prof[6] = clock64();
 }
 
 // ----------------------------------------------------------------------------- host

@@ -31,6 +31,9 @@ struct GemmEpilogue {
   int64_t ld_target = 0;
   float* loss_slot = nullptr;             // += loss * loss_scale
   float loss_scale = 1.f;                 // 1/M (CE) or 1/(M*N) (MSE)
+  // optional phase timestamps (SM clock64): [cta][8] = start, prologue done, dependencies met,
+  // first operand tile landed, accumulator complete, epilogue done
+  long long* prof = nullptr;
 };
 
 struct StepState;                         // kernels.h

@@ -94,4 +94,40 @@ int publish_params(const UpdateArgs& a, cudaStream_t stream);   // (re)build bf1
 int allreduce_sum_f32(float* const* bufs, uint32_t* const* flags, StepState* state, int world, int rank, int64_t n,
                       int use_twoshot, cudaStream_t stream);
 
+// ---- comm_hw.cu (asynchronous parameter-server mode over peer memory)
+constexpr int HW_MAX_STRIPES = 64;
+// control block (uint32 words) in every rank's symmetric memory
+constexpr int HW_CTRL_LOCKS = 0;                        // [HW_MAX_STRIPES] stripe spin locks of the owned shard
+constexpr int HW_CTRL_STEPS = HW_MAX_STRIPES;           // [HW_MAX_STRIPES] optimizer steps applied per stripe
+constexpr int HW_CTRL_STOP = 2 * HW_MAX_STRIPES;        // stop flag (replicated on every rank)
+constexpr int HW_CTRL_PUSHES = HW_CTRL_STOP + 1;        // rank 0: total pushes
+constexpr int HW_CTRL_WIN_SUM = HW_CTRL_STOP + 2;       // rank 0: float loss window sum
+constexpr int HW_CTRL_WIN_CNT = HW_CTRL_STOP + 3;
+constexpr int HW_CTRL_ES_LOCK = HW_CTRL_STOP + 4;
+constexpr int HW_CTRL_ES_SEEDED = HW_CTRL_STOP + 5;
+constexpr int HW_CTRL_ES_BEST = HW_CTRL_STOP + 6;       // float
+constexpr int HW_CTRL_ES_BAD = HW_CTRL_STOP + 7;
+constexpr int HW_CTRL_WORDS = HW_CTRL_STOP + 16;
+
+struct HogwildArgs {
+  int world, rank, stripes;
+  float* param[8];            // owner r's fp32 arena (only shard r is authoritative)
+  float* m[8];
+  float* v[8];
+  uint32_t* ctrl[8];
+  float* local_param;         // pulled snapshot (the module's parameters are views of it)
+  const float* local_grad;    // this worker's gradient arena
+  const float* loss_in;       // [0] train loss, [1] validation loss of this iteration
+  int use_val_loss;
+  int64_t numel;
+  int acquire_lock;
+  int kind;
+  float lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  int nesterov, maximize;
+  int patience, window_len;
+  volatile uint32_t* host_mailbox;
+};
+int hogwild_pull(const HogwildArgs& a, cudaStream_t stream);
+int hogwild_push(const HogwildArgs& a, cudaStream_t stream);
+
 }  // namespace st

@@ -166,6 +166,56 @@ def handle_model(
     return "finished"
 
 
+# ------------------------------------------------------------------ GPU-resident variant
+def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_patience=-1, mini_batch=-1,
+                     validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4):
+    """Barrier-task body of ``mode='hogwild', device='cuda'``: no HTTP, the GPUs' own
+    memory is the parameter server (parallel/hogwild_p2p.py)."""
+    from pyspark.taskcontext import BarrierTaskContext
+
+    from sparktorch_b200.parallel import rendezvous
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild
+    from sparktorch_b200.runtime.engine import TrainConfig
+
+    context = BarrierTaskContext.get()
+    dev = resolve_device(device, context.partitionId())
+    torch.cuda.set_device(dev)
+    rank, world = rendezvous.init_from_barrier(context, dev)
+    try:
+        raw = load_torch_model(torch_obj, build_optimizer=False)
+        X, Y = rows_to_block(data)
+        if X is None:
+            raise RuntimeError(f"partition {index} is empty")
+        cfg = TrainConfig(iters=iters, mini_batch=mini_batch, validation_pct=validation_pct,
+                          early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev), seed=seed)
+        res = train_partition_hogwild(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y,
+                                      cfg, dev, acquire_lock, window_len)
+    finally:
+        rendezvous.shutdown()
+    return [{"state_dict": res.state_dict, "history": res.history}] if rank == 0 else []
+
+
+def train_gpu(rdd, torch_obj, iters=10, partition_shuffles=1, verbose=1, early_stop_patience=-1, mini_batch=-1,
+              validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4):
+    from sparktorch_b200.distributed import _reseed_blob, mapPartitionsWithIndex
+
+    blob, _ = load_base_torch(torch_obj)
+    state_dict = history = None
+    for r in range(partition_shuffles):
+        def task(i, x, blob=blob):
+            return handle_model_gpu(i, x, blob, iters=iters, verbose=verbose, early_stop_patience=early_stop_patience,
+                                    mini_batch=mini_batch, validation_pct=validation_pct, device=device, seed=seed,
+                                    acquire_lock=acquire_lock, window_len=window_len)
+
+        task._accepts_blocks = True
+        out = mapPartitionsWithIndex(rdd, task).collect()
+        state_dict, history = out[0]["state_dict"], out[0]["history"]
+        if partition_shuffles - r > 1:
+            rdd = rdd.repartition(rdd.getNumPartitions())
+            blob = _reseed_blob(blob, state_dict)       # weights carry over, like the persistent server
+    return state_dict, history
+
+
 # ------------------------------------------------------------------ driver
 def train(
     rdd: RDD,

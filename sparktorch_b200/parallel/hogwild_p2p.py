@@ -1,0 +1,138 @@
+"""GPU-resident hogwild: the parameter server is the NVLink-connected memory of
+the GPUs (kernels in csrc/comm_hw.cu).  One barrier task per GPU; inside, workers
+never wait for each other: pull (P2P all-gather of the owner shards) → forward /
+backward on the local mini-batch → push (remote optimizer step on every owner's
+shard).  Replaces the reference's Flask server + dill-over-HTTP transport
+(hogwild.py:96-140, server.py:95-149) on a single NVSwitch domain; across nodes or
+on CPU the HTTP parameter server (sparktorch_b200/server.py) is used instead.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from sparktorch_b200.ops import native
+from sparktorch_b200.parallel.p2p import SymmBlock
+from sparktorch_b200.runtime.engine import DeviceSampler, EagerStep, FitResult, TrainConfig, prepare_targets
+from sparktorch_b200.runtime.flat import TAIL, FlatArena
+from sparktorch_b200.runtime.optim import parse_optimizer
+from sparktorch_b200.util import split_validation
+
+
+def pick_stripes(numel: int, world: int, max_stripes: int) -> int:
+    per = (numel // 4 + world - 1) // world
+    return int(max(1, min(max_stripes, per // 2048)))
+
+
+def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, opt_cls, opt_params: Optional[Dict],
+                            X: np.ndarray, Y: Optional[np.ndarray], cfg: TrainConfig, device: torch.device,
+                            acquire_lock: bool, window_len: int) -> FitResult:
+    C = native.load(required=True)
+    spec = parse_optimizer(opt_cls, opt_params)
+    if spec.kind == "other":
+        raise RuntimeError("GPU hogwild supports SGD/Adam/AdamW; other optimizers use the HTTP parameter server")
+    t_start = time.time()
+    torch.cuda.set_device(device)
+    rng = np.random.default_rng(None if cfg.seed is None else cfg.seed + 7919 * rank)
+
+    # ---- data ----------------------------------------------------------------------------
+    xt = torch.from_numpy(X)
+    yt = torch.from_numpy(Y) if Y is not None else None
+    x_val = y_val = None
+    if cfg.validation_pct > 0:
+        tr, va = split_validation(X.shape[0], cfg.validation_pct, rng)
+        if len(va):
+            x_val = xt[torch.from_numpy(va)].to(device)
+            y_val = prepare_targets(yt[torch.from_numpy(va)].to(device), criterion) if yt is not None else x_val
+            xt = xt[torch.from_numpy(tr)]
+            yt = yt[torch.from_numpy(tr)] if yt is not None else None
+    x_all = xt.to(device)
+    y_all = prepare_targets(yt.to(device), criterion) if yt is not None else x_all
+    n = x_all.shape[0]
+
+    # ---- model + arenas ------------------------------------------------------------------------
+    model = model.to(device).train()
+    if hasattr(criterion, "to"):
+        criterion = criterion.to(device)
+    numel = FlatArena.measure(model)
+    blk = SymmBlock(device, world, rank)
+    blk.reserve("param", numel * 4)
+    if spec.n_state >= 1:
+        blk.reserve("m", numel * 4)
+    if spec.n_state >= 2:
+        blk.reserve("v", numel * 4)
+    blk.reserve("ctrl", C.hw_ctrl_words() * 4)
+    blk.rendezvous()
+    owner_param = blk.view("param", torch.float32, numel)
+    local_p = torch.zeros(numel, device=device)
+    local_g = torch.zeros(numel + TAIL, device=device)
+    arena = FlatArena(model, device, grad_buffer=local_g, param_buffer=local_p)
+    if world > 1:
+        dist.broadcast(local_p, src=0)            # the job starts from rank 0's weights
+    owner_param.copy_(local_p)
+    loss_in = torch.zeros(2, device=device)
+    mailbox = torch.zeros(4, dtype=torch.int32).pin_memory()
+    stripes = pick_stripes(numel, world, C.hw_max_stripes())
+    worker = C.HogwildWorker(
+        world, rank, stripes, blk.peer_ptrs("param"), blk.peer_ptrs("m") if spec.n_state >= 1 else [],
+        blk.peer_ptrs("v") if spec.n_state >= 2 else [], blk.peer_ptrs("ctrl"), local_p, local_g, loss_in,
+        x_val is not None, numel, bool(acquire_lock), spec.kind_id, spec.lr, spec.beta1, spec.beta2, spec.eps,
+        spec.weight_decay, spec.momentum, spec.dampening, spec.nesterov, spec.maximize, cfg.early_stop_patience,
+        max(1, window_len), mailbox.data_ptr())
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+
+    step = EagerStep(model, criterion, arena)
+    use_mb = 0 < cfg.mini_batch < n
+    sampler = DeviceSampler(n, cfg.mini_batch, device, None if cfg.seed is None else cfg.seed + rank) if use_mb else None
+    loss_hist = torch.zeros(max(1, cfg.iters), device=device)
+    t_loop = time.time()
+    stopped_at = None
+    done = 0
+    for i in range(cfg.iters):
+        if sampler is not None:
+            idx = sampler.next()
+            xb = x_all[idx]
+            yb = xb if y_all is x_all else y_all[idx]
+        else:
+            xb, yb = x_all, y_all
+        worker.pull()                              # P2P all-gather of the owners' shards
+        loss = step.run(xb, yb)
+        loss_in[0] = loss
+        if x_val is not None:
+            loss_in[1] = step.evaluate(x_val, y_val)
+        loss_hist[i] = loss
+        worker.push()                              # remote optimizer step on every owner's shard
+        done = i + 1
+        if cfg.verbose:
+            print(f"Partition: {rank}. Iteration: {i}. Loss: {float(loss)}, "
+                  f"Val Loss: {float(loss_in[1]) if x_val is not None else None}")
+        if cfg.early_stop_patience > 0:
+            torch.cuda.current_stream(device).synchronize()
+            if int(mailbox[0]) != 0:
+                stopped_at = i
+                break
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()                             # every worker has pushed its last gradient
+    worker.pull()
+    torch.cuda.synchronize(device)
+    t_end = time.time()
+    ctrl0 = blk.view("ctrl", torch.int32, C.hw_ctrl_words())
+    history = {
+        "engine": "eager", "comm": "HogwildP2P" + ("+locks" if acquire_lock else ""), "world_size": world,
+        "train_loss": loss_hist[:done].cpu().tolist(), "stopped_at": stopped_at, "iters_run": done,
+        "samples_per_step": (cfg.mini_batch if use_mb else n), "stripes": stripes,
+        "pushes_total": int(ctrl0[2 * C.hw_max_stripes() + 1]) if rank == 0 else None,
+        "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
+    }
+    state = arena.detach_state_dict() if rank == 0 else None
+    if world > 1:
+        dist.barrier()                             # keep peer memory alive until everyone has read it
+    return FitResult(state, history)

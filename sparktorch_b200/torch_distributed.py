@@ -269,6 +269,14 @@ class SparkTorch(Estimator, HasInputCol, HasPredictionCol, HasLabelCol, PysparkR
                 device=device, early_stop_patience=self.getEarlyStopPatience(), compile_mode=self.getCompileMode(),
                 precision=precision, engine=engine, seed=seed, streaming=streaming, return_history=True,
                 time_window=getattr(self, "_time_window", None), sampling=_param_or(self, "sampling", "random"))
+        elif mode == "hogwild" and str(device).startswith("cuda"):
+            from sparktorch_b200.hogwild import train_gpu
+
+            state_dict, history = train_gpu(
+                rdd, torch_obj, self.getIters(), self.getPartitionShuffles(), verbose=self.getVerbose(),
+                early_stop_patience=self.getEarlyStopPatience(), mini_batch=self.getMiniBatch(),
+                validation_pct=self.getValidationPct(), device=device, seed=seed,
+                acquire_lock=self.getAqcuireLock(), window_len=partitions)
         elif mode == "hogwild":
             from sparktorch_b200.hogwild import get_main, train
             from sparktorch_b200.server import Server
