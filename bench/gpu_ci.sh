@@ -6,4 +6,5 @@ run() { name=$1; shift; echo "=== $name"; timeout 420 python -m pytest -m gpu -q
 run gemm_k tests/test_gpu_kernels.py -k "gemm and (False-False or block_n or deep_k or forward_epilogue)"
 run gemm_mn tests/test_gpu_kernels.py -k "gemm and not (False-False or block_n or deep_k or forward_epilogue)"
 run misc tests/test_gpu_kernels.py -k "not gemm"
+run conv tests/test_gpu_kernels.py -k "im2col or conv or maxpool"
 run engine tests/test_gpu_engine.py

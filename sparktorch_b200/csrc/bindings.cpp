@@ -120,6 +120,56 @@ void transpose_bf16(const Tensor& src, int64_t rows, int64_t cols, const Tensor&
   check(st::transpose_bf16(bf16p(src), src.stride(0), int(rows), int(cols), bf16pm(dst), dst.stride(0), cur_stream()), "transpose_bf16");
 }
 
+// ------------------------------------------------------------------ convolution helpers
+void im2col_nhwc(const Tensor& x, int64_t B, int64_t H, int64_t W, int64_t Cc, int64_t sb, int64_t sh, int64_t sw, int64_t sc,
+                 int64_t kh, int64_t kw, int64_t stride, int64_t pad, const Tensor& col, const OptT& state, int64_t window_rows,
+                 int64_t n_windows) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16);
+  req_2d(col, at::kBFloat16, "col");
+  c10::cuda::CUDAGuard guard(x.device());
+  st::Im2colArgs a{};
+  a.x = bf16p(x); a.sb = sb; a.sh = sh; a.sw = sw; a.sc = sc;
+  a.state = state ? reinterpret_cast<const st::StepState*>(state->data_ptr()) : nullptr;
+  a.window_rows = window_rows; a.n_windows = n_windows > 0 ? n_windows : 1;
+  a.B = int(B); a.H = int(H); a.W = int(W); a.C = int(Cc);
+  a.kh = int(kh); a.kw = int(kw); a.stride = int(stride); a.pad = int(pad);
+  a.OH = int((H + 2 * pad - kh) / stride + 1); a.OW = int((W + 2 * pad - kw) / stride + 1);
+  a.K = int(Cc * kh * kw); a.col = bf16pm(col); a.ld_col = col.stride(0);
+  TORCH_CHECK(col.size(0) >= B * a.OH * a.OW && col.stride(0) >= a.K, "col buffer too small");
+  check(st::im2col_nhwc(a, cur_stream()), "im2col_nhwc");
+}
+
+void flip_conv_weight(const Tensor& w, int64_t Cout, int64_t Cin, int64_t kh, int64_t kw, const Tensor& out) {
+  req_2d(w, at::kBFloat16, "w");
+  req_2d(out, at::kBFloat16, "out");
+  c10::cuda::CUDAGuard guard(w.device());
+  check(st::flip_conv_weight(bf16p(w), w.stride(0), int(Cout), int(Cin), int(kh), int(kw), bf16pm(out), out.stride(0), cur_stream()),
+        "flip_conv_weight");
+}
+
+void maxpool_dropout(bool backward, const Tensor& x_or_dx, int64_t ld_x, const Tensor& y_or_dy, const Tensor& idx, int64_t B,
+                     int64_t H, int64_t W, int64_t Cc, int64_t k, double p_drop, bool train, int64_t seed, const OptT& state,
+                     bool y_nhwc, const OptT& relu_x, const OptT& db) {
+  req_2d(y_or_dy, at::kBFloat16, "y");
+  TORCH_CHECK(x_or_dx.scalar_type() == at::kBFloat16 && idx.scalar_type() == at::kByte);
+  c10::cuda::CUDAGuard guard(x_or_dx.device());
+  st::PoolArgs a{};
+  a.B = int(B); a.H = int(H); a.W = int(W); a.C = int(Cc); a.k = int(k); a.PH = int(H / k); a.PW = int(W / k);
+  a.p_drop = float(p_drop); a.train = train; a.seed = uint64_t(seed);
+  a.state = state ? reinterpret_cast<const st::StepState*>(state->data_ptr()) : nullptr;
+  a.idx = idx.data_ptr<uint8_t>();
+  a.y_nhwc = y_nhwc;
+  a.relu_x = relu_x ? bf16p(*relu_x) : nullptr;
+  a.db = db ? db->data_ptr<float>() : nullptr;
+  if (!backward) {
+    a.x = bf16p(x_or_dx); a.ld_x = ld_x; a.y = bf16pm(y_or_dy); a.ld_y = y_or_dy.stride(0);
+    check(st::maxpool_dropout_fwd(a, cur_stream()), "maxpool_dropout_fwd");
+  } else {
+    a.dx = bf16pm(x_or_dx); a.ld_dx = ld_x; a.dy = bf16p(y_or_dy); a.ld_dy = y_or_dy.stride(0);
+    check(st::maxpool_dropout_bwd(a, cur_stream()), "maxpool_dropout_bwd");
+  }
+}
+
 // ------------------------------------------------------------------ fused all-reduce + optimizer
 class Updater {
  public:
@@ -327,6 +377,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);
   m.def("transpose_bf16", &transpose_bf16);
+  m.def("im2col_nhwc", &im2col_nhwc, py::arg("x"), py::arg("B"), py::arg("H"), py::arg("W"), py::arg("C"), py::arg("sb"),
+        py::arg("sh"), py::arg("sw"), py::arg("sc"), py::arg("kh"), py::arg("kw"), py::arg("stride"), py::arg("pad"),
+        py::arg("col"), py::arg("state") = py::none(), py::arg("window_rows") = 0, py::arg("n_windows") = 1);
+  m.def("flip_conv_weight", &flip_conv_weight);
+  m.def("maxpool_dropout", &maxpool_dropout, py::arg("backward"), py::arg("x_or_dx"), py::arg("ld_x"), py::arg("y_or_dy"),
+        py::arg("idx"), py::arg("B"), py::arg("H"), py::arg("W"), py::arg("C"), py::arg("k"), py::arg("p_drop") = 0.0,
+        py::arg("train") = false, py::arg("seed") = 0, py::arg("state") = py::none(), py::arg("y_nhwc") = false,
+        py::arg("relu_x") = py::none(), py::arg("db") = py::none());
   m.def("allreduce_sum", &allreduce_sum);
   m.def("pack_segments", &pack_segments);
   m.def("step_state_bytes", &step_state_bytes);

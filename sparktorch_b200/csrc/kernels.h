@@ -94,6 +94,41 @@ int publish_params(const UpdateArgs& a, cudaStream_t stream);   // (re)build bf1
 int allreduce_sum_f32(float* const* bufs, uint32_t* const* flags, StepState* state, int world, int rank, int64_t n,
                       int use_twoshot, cudaStream_t stream);
 
+// ---- conv.cu
+struct Im2colArgs {
+  const __nv_bfloat16* x;     // image batch addressed as x[b*sb + h*sh + w*sw + c*sc]
+  int64_t sb, sh, sw, sc;
+  const StepState* state;     // optional device-side batch window (sample offset)
+  int64_t window_rows, n_windows;
+  int B, H, W, C, kh, kw, stride, pad, OH, OW, K;   // K = C*kh*kw, columns in (c, i, j) order
+  __nv_bfloat16* col;         // [B*OH*OW, ld_col]
+  int64_t ld_col;
+};
+int im2col_nhwc(const Im2colArgs& a, cudaStream_t stream);
+int flip_conv_weight(const __nv_bfloat16* w, int64_t ld_w, int Cout, int Cin, int kh, int kw, __nv_bfloat16* out, int64_t ld_o,
+                     cudaStream_t stream);
+struct PoolArgs {
+  const __nv_bfloat16* x;     // fwd input NHWC [B, H, W, C]
+  int64_t ld_x;
+  __nv_bfloat16* y;           // fwd output [B, ld_y], (c, ph, pw) order
+  int64_t ld_y;
+  uint8_t* idx;               // [B, PH, PW, C]
+  const __nv_bfloat16* dy;    // bwd input, same layout as y
+  int64_t ld_dy;
+  __nv_bfloat16* dx;          // bwd output NHWC
+  int64_t ld_dx;
+  int B, H, W, C, k, PH, PW;
+  int y_nhwc;                 // pooled layout: 1 NHWC (feeds another conv), 0 (c, ph, pw) = torch flatten order
+  const __nv_bfloat16* relu_x;  // bwd: forward input (post-ReLU) to mask the gradient, or null
+  float* db;                  // bwd: += per-channel sums of dx (bias gradient of the producing conv), or null
+  float p_drop;
+  int train;
+  uint64_t seed;
+  const StepState* state;
+};
+int maxpool_dropout_fwd(const PoolArgs& a, cudaStream_t stream);
+int maxpool_dropout_bwd(const PoolArgs& a, cudaStream_t stream);
+
 // ---- comm_hw.cu (asynchronous parameter-server mode over peer memory)
 constexpr int HW_MAX_STRIPES = 64;
 // control block (uint32 words) in every rank's symmetric memory

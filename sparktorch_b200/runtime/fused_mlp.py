@@ -336,12 +336,21 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     if spec.kind == "other" or world > 8:
         return None
     lowered = lower_mlp(model)
+    is_cnn = False
+    if lowered is None:
+        from sparktorch_b200.runtime.fused_cnn import lower_cnn
+
+        lowered = lower_cnn(model, X.shape[1])
+        is_cnn = lowered is not None
     if lowered is None:
         return None
     kind = loss_kind(criterion, lowered)
     if kind is None:
         return None
-    d0, dL = lowered.layers[0].module.in_features, lowered.layers[-1].module.out_features
+    if is_cnn:
+        d0, dL = X.shape[1], lowered.linears[-1].module.out_features
+    else:
+        d0, dL = lowered.layers[0].module.in_features, lowered.layers[-1].module.out_features
     if X.shape[1] != d0:
         return None
     if kind == "mse":
@@ -372,7 +381,13 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     nv = 0 if x_val is None else x_val.shape[0]
 
     model = model.to(device)
-    plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1)
+    if is_cnn:
+        from sparktorch_b200.runtime.fused_cnn import FusedCNN
+
+        plan = FusedCNN(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1,
+                        seed=0 if cfg.seed is None else int(cfg.seed))
+    else:
+        plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1)
     if world > 1:
         import torch.distributed as dist
 
@@ -509,7 +524,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     stopped = plan.fu.stopped()
     losses = plan.fu.loss_hist[:n_done].cpu().tolist()
     history = {
-        "engine": "fused_mlp", "comm": "P2PFused" + ("+NVLS" if plan.fu.use_multicast else ""), "precision": "bf16",
+        "engine": "fused_cnn" if is_cnn else "fused_mlp", "comm": "P2PFused" + ("+NVLS" if plan.fu.use_multicast else ""), "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
         "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
         "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes(),

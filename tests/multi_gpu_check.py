@@ -116,6 +116,20 @@ def main():
     allst = [torch.zeros_like(stops) for _ in range(world)]
     dist.all_gather(allst, stops)
     assert all(int(s) == int(allst[0]) and int(s) >= 2 for s in allst), allst
+    # ---- 4. hogwild over peer memory: no barriers between workers, remote optimizer steps -------------
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild
+
+    for lock in (True, False):
+        cfg = TrainConfig(iters=60, mini_batch=128, device="cuda", seed=9)
+        hw = train_partition_hogwild(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3},
+                                     X, Y, cfg, dev, acquire_lock=lock, window_len=world)
+        hh = hw.history
+        assert np.isfinite(hh["train_loss"]).all() and np.mean(hh["train_loss"][-8:]) < 0.8 * np.mean(hh["train_loss"][:3]), hh["train_loss"][::10]
+        if rank == 0:
+            assert hh["pushes_total"] == 60 * world, hh["pushes_total"]
+            assert all(torch.isfinite(v).all() for v in hw.state_dict.values())
+            print(f"hogwild lock={lock} ok: pushes={hh['pushes_total']} stripes={hh['stripes']} loss {hh['train_loss'][0]:.3f}->{hh['train_loss'][-1]:.3f}", flush=True)
+        dist.barrier()
     dist.barrier()
     if rank == 0:
         print("fused fit ok:", [round(v, 3) for v in h["train_loss"][::20]], "comm", h["comm"], flush=True)

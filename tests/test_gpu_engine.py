@@ -20,7 +20,8 @@ def _fit(model, crit, opt, kw, X, Y, **cfgkw):
     from sparktorch_b200.runtime.engine import TrainConfig, train_partition
 
     dev = torch.device("cuda", 0)
-    cfg = TrainConfig(device="cuda", seed=0, **cfgkw)
+    cfgkw.setdefault("seed", 0)
+    cfg = TrainConfig(device="cuda", **cfgkw)
     return train_partition(0, 1, model, crit, opt, kw, X, Y, cfg, dev)
 
 
@@ -163,3 +164,107 @@ def test_spark_api_on_gpu_and_batched_inference(tmp_path):
     f = try_fused_predictor(net, torch.device("cuda", 0))
     xb = torch.from_numpy(X[:300]).cuda()
     torch.testing.assert_close(f(xb), net(xb), rtol=5e-2, atol=5e-2)
+
+
+def test_hogwild_gpu_single_worker_equals_sequential_adam():
+    """One worker, striped locks: pull -> grad -> remote push is plain sequential Adam."""
+    import copy
+
+    from sparktorch_b200.models import MnistCNN
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild
+    from sparktorch_b200.runtime.engine import TrainConfig
+
+    rng = np.random.default_rng(5)
+    X = rng.random((512, 784)).astype(np.float32)
+    Y = rng.integers(0, 10, size=(512, 1)).astype(np.float32)
+    torch.manual_seed(3)
+    net = MnistCNN(p_drop=0.0)
+    dev = torch.device("cuda", 0)
+    cfg = TrainConfig(iters=15, mini_batch=64, device="cuda", seed=11)
+    hw = train_partition_hogwild(0, 1, copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, cfg,
+                                 dev, acquire_lock=True, window_len=1)
+    ref = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=15, mini_batch=64, engine="eager",
+               comm="collective", seed=11)
+    assert hw.history["comm"].startswith("HogwildP2P") and hw.history["pushes_total"] == 15
+    np.testing.assert_allclose(hw.history["train_loss"], ref.history["train_loss"], rtol=2e-3, atol=2e-4)
+    for k in ref.state_dict:
+        torch.testing.assert_close(hw.state_dict[k], ref.state_dict[k], rtol=1e-3, atol=1e-4)
+
+
+def test_hogwild_gpu_through_spark_api_with_early_stop():
+    import sparktorch_b200  # noqa: F401
+    from pyspark.sql import SparkSession
+    from sparktorch_b200 import SparkTorch, serialize_torch_obj
+    from tests.nets import Classifier
+
+    spark = SparkSession.builder.master("local[1]").getOrCreate()
+    rng = np.random.default_rng(0)
+    X = np.concatenate([rng.normal(0, 1, (200, 10)), rng.normal(2, 1, (200, 10))]).astype(np.float32)
+    y = np.concatenate([np.ones(200), np.zeros(200)])
+    df = spark.createDataFrame({"label": y, "features": X}, numPartitions=1)
+    obj = serialize_torch_obj(Classifier(), nn.CrossEntropyLoss(), torch.optim.Adam, lr=0.02)
+    stm = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj, iters=80,
+                     mode="hogwild", device="cuda", miniBatch=64, earlyStopPatience=60, seed=2).fit(df)
+    assert stm.getTrainingHistory()["comm"].startswith("HogwildP2P")
+    rows = stm.transform(df).collect()
+    assert np.mean([r["predictions"] == r["label"] for r in rows]) > 0.9
+
+
+def test_fused_cnn_tracks_eager_on_mnist_cnn():
+    import copy
+
+    from sparktorch_b200.models import MnistCNN
+
+    rng = np.random.default_rng(6)
+    protos = (rng.random((10, 784)) < 0.2).astype(np.float32)
+    lab = rng.integers(0, 10, size=512)
+    X = (protos[lab] * rng.random((512, 784)) * 2).astype(np.float32)
+    Y = lab.astype(np.float32).reshape(-1, 1)
+    torch.manual_seed(5)
+    net = MnistCNN(p_drop=0.0)
+    ref = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=20, engine="eager",
+               comm="collective", precision="fp32")
+    got = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=20, engine="fused")
+    assert got.history["engine"] == "fused_cnn"
+    a, b = np.array(got.history["train_loss"]), np.array(ref.history["train_loss"])
+    np.testing.assert_allclose(a[0], b[0], rtol=3e-2)
+    np.testing.assert_allclose(a, b, rtol=0.15, atol=0.03)
+    assert a[-1] < 0.8 * a[0]
+    # with dropout2d and mini-batches it still learns
+    res = _fit(MnistCNN(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=120, mini_batch=128, engine="fused",
+               sampling="sweep")
+    assert res.history["engine"] == "fused_cnn"
+    assert np.mean(res.history["train_loss"][-10:]) < 0.6 * np.mean(res.history["train_loss"][:3])
+
+
+def test_fused_cnn_lenet_chain_conv_pool_conv():
+    import copy
+
+    class LeNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = nn.Conv2d(1, 6, 5, padding=2)
+            self.c2 = nn.Conv2d(6, 16, 5)
+            self.p = nn.MaxPool2d(2)
+            self.f1 = nn.Linear(400, 120)
+            self.f2 = nn.Linear(120, 10)
+
+        def forward(self, x):
+            x = x.view(-1, 1, 28, 28)
+            x = self.p(torch.relu(self.c1(x)))
+            x = self.p(torch.relu(self.c2(x)))
+            x = torch.flatten(x, 1)
+            return self.f2(torch.relu(self.f1(x)))
+
+    rng = np.random.default_rng(8)
+    protos = (rng.random((10, 784)) < 0.2).astype(np.float32)
+    lab = rng.integers(0, 10, size=256)
+    X = (protos[lab] * rng.random((256, 784)) * 2).astype(np.float32)
+    Y = lab.astype(np.float32).reshape(-1, 1)
+    torch.manual_seed(9)
+    net = LeNet()
+    ref = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=15, engine="eager",
+               comm="collective", precision="fp32")
+    got = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=15, engine="fused")
+    assert got.history["engine"] == "fused_cnn"
+    np.testing.assert_allclose(got.history["train_loss"], ref.history["train_loss"], rtol=0.15, atol=0.03)

@@ -377,3 +377,93 @@ def test_publish_only_builds_bf16_copies(C):
     torch.cuda.synchronize()
     assert torch.equal(param, before)
     torch.testing.assert_close(wb.view(rows, cols).float(), param.view(rows, cols).to(torch.bfloat16).float(), rtol=0, atol=0)
+
+
+def test_im2col_matches_unfold(C):
+    import torch.nn.functional as F
+
+    B, Cin, H, W, kh, kw = 5, 3, 12, 10, 3, 3
+    for stride, pad in ((1, 0), (1, 1), (2, 1), (1, 2)):
+        x = torch.randn(B, Cin, H, W, device=dev()).to(torch.bfloat16)
+        ref = F.unfold(x.float(), (kh, kw), padding=pad, stride=stride)          # [B, Cin*kh*kw, L]
+        OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+        K = Cin * kh * kw
+        # NCHW source (torch row layout)
+        col = torch.full((B * OH * OW, _pad8(K)), 9.0, dtype=torch.bfloat16, device=dev())[:, :K]
+        xf = x.reshape(B, -1)
+        C.im2col_nhwc(xf, B, H, W, Cin, xf.stride(0), W, 1, H * W, kh, kw, stride, pad, col)
+        got = col.float().view(B, OH * OW, K).permute(0, 2, 1)
+        torch.testing.assert_close(got, ref, rtol=0, atol=0)
+        # NHWC source
+        xn = x.permute(0, 2, 3, 1).contiguous()
+        col2 = torch.zeros_like(col)
+        C.im2col_nhwc(xn, B, H, W, Cin, H * W * Cin, W * Cin, Cin, 1, kh, kw, stride, pad, col2)
+        torch.testing.assert_close(col2.float(), col.float(), rtol=0, atol=0)
+
+
+def test_conv_forward_and_backward_via_gemm(C):
+    """conv fwd = im2col+GEMM; wgrad = dY^T col; dgrad = im2col(pad) of dY x flipped taps  vs  autograd."""
+    import torch.nn.functional as F
+
+    B, Cin, H, W, Cout, k, pad = 4, 16, 12, 12, 32, 3, 1
+    x = (torch.randn(B, Cin, H, W, device=dev()) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev()) * 0.1).to(torch.bfloat16)
+    b = torch.randn(Cout, device=dev())
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, b, padding=pad)
+    gy = (torch.randn_like(y_ref) * 0.1).to(torch.bfloat16)
+    y_ref.backward(gy.float())
+    OH = OW = H + 2 * pad - k + 1
+    K = Cin * k * k
+    xn = x.permute(0, 2, 3, 1).contiguous()                       # NHWC
+    col = torch.zeros(B * OH * OW, K, dtype=torch.bfloat16, device=dev())
+    C.im2col_nhwc(xn, B, H, W, Cin, H * W * Cin, W * Cin, Cin, 1, k, k, 1, pad, col)
+    w2 = w.reshape(Cout, K).contiguous()
+    y = torch.zeros(B * OH * OW, Cout, dtype=torch.bfloat16, device=dev())
+    C.gemm_bf16(col, False, w2, False, B * OH * OW, Cout, K, bias=b, out_bf16=y)
+    torch.testing.assert_close(y.float().view(B, OH, OW, Cout).permute(0, 3, 1, 2), y_ref.detach(), rtol=3e-2, atol=3e-2)
+    # wgrad
+    gyn = gy.permute(0, 2, 3, 1).reshape(B * OH * OW, Cout).contiguous()
+    dw = torch.zeros(Cout, K, device=dev())
+    C.gemm_bf16(gyn, True, col, True, Cout, K, B * OH * OW, out_f32=dw, atomic_f32=True, split_k=4)
+    torch.testing.assert_close(dw.view(Cout, Cin, k, k), wr.grad, rtol=3e-2, atol=3e-2)
+    # dgrad
+    wf = torch.zeros(Cin, Cout * k * k, dtype=torch.bfloat16, device=dev())
+    C.flip_conv_weight(w2, Cout, Cin, k, k, wf)
+    colT = torch.zeros(B * H * W, Cout * k * k, dtype=torch.bfloat16, device=dev())
+    C.im2col_nhwc(gyn, B, OH, OW, Cout, OH * OW * Cout, OW * Cout, Cout, 1, k, k, 1, k - 1 - pad, colT)
+    dx = torch.zeros(B * H * W, Cin, dtype=torch.bfloat16, device=dev())
+    C.gemm_bf16(colT, False, wf, False, B * H * W, Cin, Cout * k * k, out_bf16=dx)
+    torch.testing.assert_close(dx.float().view(B, H, W, Cin).permute(0, 3, 1, 2), xr.grad, rtol=3e-2, atol=3e-2)
+
+
+def test_maxpool_dropout_kernels(C):
+    import torch.nn.functional as F
+
+    B, Cc, H, W, k = 6, 32, 22, 22, 2
+    x = torch.randn(B, Cc, H, W, device=dev()).to(torch.bfloat16)
+    xn = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cc)
+    PH, PW = H // k, W // k
+    y = torch.zeros(B, Cc * PH * PW, dtype=torch.bfloat16, device=dev())
+    idx = torch.zeros(B * PH * PW * Cc, dtype=torch.uint8, device=dev())
+    C.maxpool_dropout(False, xn, Cc, y, idx, B, H, W, Cc, k)
+    xr = x.float().requires_grad_(True)
+    ref = F.max_pool2d(xr, k)
+    torch.testing.assert_close(y.float().view(B, Cc, PH, PW), ref.detach(), rtol=0, atol=0)
+    gy = torch.randn(B, Cc * PH * PW, device=dev()).to(torch.bfloat16)
+    ref.backward(gy.float().view(B, Cc, PH, PW))
+    dx = torch.full((B * H * W, Cc), 5.0, dtype=torch.bfloat16, device=dev())
+    db = torch.zeros(Cc, device=dev())
+    C.maxpool_dropout(True, dx, Cc, gy, idx, B, H, W, Cc, k, db=db)
+    torch.testing.assert_close(dx.float().view(B, H, W, Cc).permute(0, 3, 1, 2), xr.grad, rtol=0, atol=0)
+    torch.testing.assert_close(db, xr.grad.sum((0, 2, 3)), rtol=1e-3, atol=1e-3)
+    # NHWC pooled layout + dropout2d statistics
+    y2 = torch.zeros(B * PH * PW, Cc, dtype=torch.bfloat16, device=dev())
+    C.maxpool_dropout(False, xn, Cc, y2, idx, B, H, W, Cc, k, p_drop=0.5, train=True, seed=7, y_nhwc=True)
+    kept = (y2.float().view(B, PH * PW, Cc).abs().sum(1) > 0)
+    frac = kept.float().mean().item()
+    assert 0.3 < frac < 0.7
+    ref2 = ref.detach().permute(0, 2, 3, 1).reshape(B, PH * PW, Cc) * 2.0
+    torch.testing.assert_close(y2.float().view(B, PH * PW, Cc)[kept.unsqueeze(1).expand(-1, PH * PW, -1)],
+                               ref2[kept.unsqueeze(1).expand(-1, PH * PW, -1)], rtol=1e-2, atol=1e-2)
