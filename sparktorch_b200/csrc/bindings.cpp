@@ -35,7 +35,8 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
                const OptT& out_f32, const OptT& out_t_f32, bool atomic_f32, const OptT& colsum, int64_t block_n,
                int64_t split_k, int64_t loss_kind, const OptT& labels, const OptT& target, const OptT& loss_slot,
                double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags,
-               const OptT& prof) {
+               const OptT& prof, const std::vector<int64_t>& peer_ptrs, int64_t peer_shard_elems, int64_t peer_w_off,
+               int64_t peer_bias_off, bool peer_fill_local) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
   c10::cuda::CUDAGuard guard(A.device());
@@ -67,8 +68,16 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
     if (win_flags & 1) a_rows_total = A.size(0);
     if (win_flags & 2) b_rows_total = B.size(0);
   }
+  st::GemmPeerB peer;
+  if (!peer_ptrs.empty()) {
+    TORCH_CHECK(peer_ptrs.size() <= 8 && peer_shard_elems > 0, "K-AG: up to 8 owners");
+    peer.world = int(peer_ptrs.size());
+    for (size_t r = 0; r < peer_ptrs.size(); ++r) peer.param[r] = reinterpret_cast<const float*>(peer_ptrs[r]);
+    peer.shard_elems = peer_shard_elems; peer.w_off = peer_w_off; peer.bias_off = peer_bias_off;
+    if (peer_fill_local) { peer.wb_local = bf16pm(B); peer.ld_wb = B.stride(0); }
+  }
   check(st::gemm_bf16(A.data_ptr(), A.stride(0), a_mn ? 1 : 0, B.data_ptr(), B.stride(0), b_mn ? 1 : 0, int(M), int(N),
-                      int(K), &ep, &win, a_rows_total, b_rows_total, int(block_n), int(split_k), cur_stream()),
+                      int(K), &ep, &win, a_rows_total, b_rows_total, int(block_n), int(split_k), cur_stream(), &peer),
         "gemm_bf16");
 }
 
@@ -372,7 +381,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("loss_kind") = 0, py::arg("labels") = py::none(), py::arg("target") = py::none(),
         py::arg("loss_slot") = py::none(), py::arg("loss_scale") = 1.0, py::arg("win_state") = py::none(),
         py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0,
-        py::arg("prof") = py::none());
+        py::arg("prof") = py::none(), py::arg("peer_ptrs") = std::vector<int64_t>{}, py::arg("peer_shard_elems") = 0,
+        py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false);
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);

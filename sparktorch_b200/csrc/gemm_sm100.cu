@@ -49,7 +49,8 @@ struct GemmSmem {
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmEpilogue ep, const GemmWindow win, int M, int N, int K, int k_blocks_per_split) {
+                    const GemmEpilogue ep, const GemmWindow win, const GemmPeerB peer, int M, int N, int K,
+                    int k_blocks_per_split) {
   using S = GemmSmem<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,7 +74,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < S::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], (!B_MN && peer.world > 0) ? 5 : 1);   // TMA (A) [+ 4 gather warps (B)]
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -112,7 +113,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const bool peer_b = !B_MN && peer.world > 0;
+        mbar_arrive_expect_tx(&full_bar[s], peer_b ? S::A_BYTES : S::STAGE_BYTES);
         const int k0 = (kb_begin + i) * BLOCK_K;
         if constexpr (A_MN) {
 #pragma unroll
@@ -123,7 +125,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if constexpr (B_MN) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + 64 * j, k0 + b_k_off);
-        } else {
+        } else if (!peer_b) {
           tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
         }
       }
@@ -163,7 +165,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // Everything that does not depend on the accumulator is fetched while the main loop runs:
     // the bias slice goes to shared memory, the first ReLU-mask chunk to registers.
     const int et = threadIdx.x - 64;           // 0..127
-    if (ep.bias != nullptr) {
+    const bool peer_b = !B_MN && peer.world > 0;
+    const bool have_bias = ep.bias != nullptr || (peer_b && peer.bias_off >= 0);
+    if (peer_b && peer.bias_off >= 0) {
+      for (int c = et; c < BLOCK_N; c += 128) {
+        const int64_t f = peer.bias_off + n0 + c;
+        s_bias[c] = (n0 + c < N) ? peer.param[f / peer.shard_elems][f] : 0.f;
+      }
+    } else if (ep.bias != nullptr) {
       for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (n0 + c < N) ? ep.bias[n0 + c] : 0.f;
     }
     const bool have_mask = ep.mask_src != nullptr;
@@ -178,6 +187,76 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     };
     load_mask(mk_next, n0);
     asm volatile("bar.sync 1, 128;" ::: "memory");   // s_bias visible to the four epilogue warps
+    if constexpr (!B_MN && BLOCK_N <= 32) {
+      if (peer_b) {
+        // ===== K-AG producer: gather this CTA's B tiles from the parameter owners over NVLink =====
+        // item = (row n, 16-byte chunk c) of a [BLOCK_N x 64] bf16 tile = 8 fp32 source values.
+        constexpr int ITEMS = (BLOCK_N * 8 + 127) / 128;     // per thread per k-block (1 or 2)
+        constexpr int DEPTH = 4;                             // k-blocks of loads in flight (hides ~2 us peer latency)
+        float4 ring[DEPTH][ITEMS][2];
+        const bool k_vec = (K & 7) == 0 && (peer.w_off & 3) == 0;
+        auto issue = [&](int i, float4 (&dst)[ITEMS][2]) {
+          const int k0 = (kb_begin + i) * BLOCK_K;
+#pragma unroll
+          for (int it = 0; it < ITEMS; ++it) {
+            const int item = et + it * 128;
+            const int n = item >> 3, c = item & 7;
+            const int gn = n0 + n, gk = k0 + c * 8;
+            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+            if (item < BLOCK_N * 8 && gn < N && gk < K) {
+              const int64_t f = peer.w_off + int64_t(gn) * K + gk;
+              if (k_vec && gk + 8 <= K) {
+                lo = ld_f4_stream(reinterpret_cast<const float4*>(peer.param[f / peer.shard_elems] + f));
+                hi = ld_f4_stream(reinterpret_cast<const float4*>(peer.param[(f + 4) / peer.shard_elems] + f + 4));
+              } else {
+                float t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = (gk + q < K) ? peer.param[(f + q) / peer.shard_elems][f + q] : 0.f;
+                lo = make_float4(t[0], t[1], t[2], t[3]);
+                hi = make_float4(t[4], t[5], t[6], t[7]);
+              }
+            }
+            dst[it][0] = lo;
+            dst[it][1] = hi;
+          }
+        };
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+          if (d < num_kb) issue(d, ring[d]);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % S::STAGES;
+          const uint32_t ph = (i / S::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sb = smem + s * S::STAGE_BYTES + S::A_BYTES;
+          const int k0 = (kb_begin + i) * BLOCK_K;
+#pragma unroll
+          for (int d = 0; d < DEPTH; ++d) {
+            if (d == i % DEPTH) {
+#pragma unroll
+              for (int it = 0; it < ITEMS; ++it) {
+                const int item = et + it * 128;
+                if (item < BLOCK_N * 8) {
+                  const int n = item >> 3, c = item & 7;
+                  const float4 lo = ring[d][it][0], hi = ring[d][it][1];
+                  uint4 w;
+                  w.x = pack_bf16x2(lo.x, lo.y); w.y = pack_bf16x2(lo.z, lo.w);
+                  w.z = pack_bf16x2(hi.x, hi.y); w.w = pack_bf16x2(hi.z, hi.w);
+                  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                  *reinterpret_cast<uint4*>(sb + n * 128 + ((c ^ (n & 7)) << 4)) = w;
+                  const int gn = n0 + n, gk = k0 + c * 8;
+                  if (peer.wb_local != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && gn < N && gk < peer.ld_wb)
+                    *reinterpret_cast<uint4*>(peer.wb_local + int64_t(gn) * peer.ld_wb + gk) = w;
+                }
+              }
+              if (i + DEPTH < num_kb) issue(i + DEPTH, ring[d]);
+            }
+          }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (prof && et == 0) prof[4] = clock64();
@@ -197,7 +276,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) {
         float v = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias != nullptr) v += s_bias[c0 + j];
+        if (have_bias) v += s_bias[c0 + j];
         if (ep.relu) v = fmaxf(v, 0.f);
         acc[j] = v;
       }
@@ -381,7 +460,7 @@ int gemm_pick_block_n(int M, int N, int b_mn) {
 
 template <int BN, bool A_MN, bool B_MN>
 static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, const GemmWindow& win,
-                             int M, int N, int K, int split_k, cudaStream_t stream) {
+                             const GemmPeerB& peer, int M, int N, int K, int split_k, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -393,18 +472,19 @@ static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const
   int kb_per = (total_kb + split_k - 1) / split_k;
   int splits = (total_kb + kb_per - 1) / kb_per;      // no empty splits
   dim3 grid((N + BN - 1) / BN, (M + BLOCK_M - 1) / BLOCK_M, splits);
-  return launch_kernel(gemm_bf16_tn_kernel<BN, A_MN, B_MN>, grid, dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, ep, win, M, N, K, kb_per);
+  return launch_kernel(gemm_bf16_tn_kernel<BN, A_MN, B_MN>, grid, dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, ep, win, peer, M, N, K, kb_per);
 }
 
 template <bool A_MN, bool B_MN>
 static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
-                               const GemmWindow& win, int M, int N, int K, int split_k, cudaStream_t stream) {
+                               const GemmWindow& win, const GemmPeerB& peer, int M, int N, int K, int split_k,
+                               cudaStream_t stream) {
   switch (block_n) {
-    case 16: if constexpr (!B_MN) return launch_bn<16, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream); break;
-    case 32: if constexpr (!B_MN) return launch_bn<32, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream); break;
-    case 64: return launch_bn<64, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
-    case 128: return launch_bn<128, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
-    case 256: return launch_bn<256, A_MN, B_MN>(ta, tb, ep, win, M, N, K, split_k, stream);
+    case 16: if constexpr (!B_MN) return launch_bn<16, A_MN, B_MN>(ta, tb, ep, win, peer, M, N, K, split_k, stream); break;
+    case 32: if constexpr (!B_MN) return launch_bn<32, A_MN, B_MN>(ta, tb, ep, win, peer, M, N, K, split_k, stream); break;
+    case 64: return launch_bn<64, A_MN, B_MN>(ta, tb, ep, win, peer, M, N, K, split_k, stream);
+    case 128: return launch_bn<128, A_MN, B_MN>(ta, tb, ep, win, peer, M, N, K, split_k, stream);
+    case 256: return launch_bn<256, A_MN, B_MN>(ta, tb, ep, win, peer, M, N, K, split_k, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -413,11 +493,19 @@ static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtenso
 // bf16, base pointers 16-byte aligned, pitches multiples of 8 elements.
 int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue* ep, const GemmWindow* winp, int64_t a_rows_total, int64_t b_rows_total, int block_n,
-              int split_k, cudaStream_t stream) {
+              int split_k, cudaStream_t stream, const GemmPeerB* peerp) {
   GemmWindow win{};
   if (winp != nullptr) win = *winp;
+  GemmPeerB peer{};
+  if (peerp != nullptr) peer = *peerp;
+  if (peer.world > 0) {
+    if (b_mn) return -6;                       // the gathered operand is K-major
+    if (block_n <= 0) block_n = N <= 16 ? 16 : 32;
+    if (block_n > 32) return -7;
+  }
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -2;
+  if ((lda & 7) || (reinterpret_cast<uintptr_t>(A) & 15)) return -2;
+  if ((peerp == nullptr || peerp->world == 0) && ((ldb & 7) || (reinterpret_cast<uintptr_t>(B) & 15))) return -2;
   if (block_n <= 0) block_n = gemm_pick_block_n(M, N, b_mn);
   if (ep->loss_kind != 0 && N > (block_n >= 32 ? 32 : 16)) return -5;   // fused loss needs the row in one chunk
   if (b_mn && block_n < 64) block_n = 64;
@@ -429,13 +517,14 @@ int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, 
   const uint64_t b_krows = (win.flags & 2) && b_rows_total > 0 ? uint64_t(b_rows_total) : uint64_t(K);
   int rc = a_mn ? make_tmap_bf16_2d(&ta, A, K, M, lda, BLOCK_K) : make_tmap_bf16_2d(&ta, A, a_rows, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = b_mn ? make_tmap_bf16_2d(&tb, B, b_krows, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
+  if (peer.world > 0) tb = ta;                 // unused by the kernel in K-AG mode
+  else rc = b_mn ? make_tmap_bf16_2d(&tb, B, b_krows, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
   if (rc) return rc;
   cudaError_t e;
-  if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
-  else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
-  else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
-  else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, win, M, N, K, split_k, stream);
+  if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
+  else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
+  else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
+  else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
   return e == cudaSuccess ? 0 : 1000 + int(e);
 }
 

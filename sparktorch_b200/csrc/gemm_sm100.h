@@ -36,6 +36,22 @@ struct GemmEpilogue {
   long long* prof = nullptr;
 };
 
+// K-AG: the B operand (a weight matrix [N, K] of the flat fp32 parameter arena) is not read from a
+// local bf16 copy but gathered inside the GEMM from the arenas of its OWNERS: the arena is sharded
+// over `world` GPUs (shard_elems each), element e lives in param[e / shard_elems].  The epilogue warps
+// act as a second producer during the main loop: 128-bit loads from peer memory (NVLink), fp32->bf16,
+// swizzled st.shared into the operand stage, mbarrier arrive.  Optionally the gathered tile is also
+// written to a local bf16 copy (wb_local) for later consumers (dgrad).
+struct GemmPeerB {
+  int world = 0;                          // 0: disabled
+  const float* param[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t shard_elems = 0;
+  int64_t w_off = 0;                      // flat offset of W[0,0]; row pitch = K
+  int64_t bias_off = -1;                  // flat offset of the bias vector (or -1)
+  __nv_bfloat16* wb_local = nullptr;      // [N, ld_wb] local bf16 copy to fill (or null)
+  int64_t ld_wb = 0;
+};
+
 struct StepState;                         // kernels.h
 
 // Mini-batch window taken on the device from StepState::iter (no gather kernel, no host in the loop).
@@ -50,6 +66,6 @@ int gemm_pick_block_n(int M, int N, int b_mn);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue* ep, const GemmWindow* win, int64_t a_rows_total, int64_t b_rows_total, int block_n,
-              int split_k, cudaStream_t stream);
+              int split_k, cudaStream_t stream, const GemmPeerB* peer = nullptr);
 
 }  // namespace st

@@ -48,6 +48,9 @@ def handle_model(
     streaming: bool = False,
     time_window=None,
     sampling: str = "random",
+    checkpoint_dir: str = None,
+    checkpoint_every: int = 0,
+    resume: bool = False,
 ) -> List[Dict]:
     """Body of one barrier task = one replica (reference distributed.py:66-205).
 
@@ -71,6 +74,7 @@ def handle_model(
             early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev),
             precision=precision, engine=engine, comm=comm, seed=seed, streaming=streaming,
             time_window=tuple(time_window) if time_window else None, sampling=sampling,
+            checkpoint_dir=checkpoint_dir, checkpoint_every=checkpoint_every, resume=resume,
         )
         res = train_partition(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y, cfg, dev)
     finally:
@@ -99,6 +103,10 @@ def train_distributed(
     return_history: bool = False,
     time_window=None,
     sampling: str = "random",
+    checkpoint_dir: str = None,
+    checkpoint_every: int = 0,
+    resume: bool = False,
+    max_stage_retries: int = 1,
 ):
     """Driver entry: run the barrier stage ``partition_shuffles`` times,
     reshuffling partitions in between and carrying the weights over (the
@@ -108,17 +116,30 @@ def train_distributed(
     for r in range(partition_shuffles):
         blob = torch_loaded
 
-        def task(i, x, blob=blob):
-            return handle_model(
-                i, x, torch_obj=blob, iters=iters, verbose=verbose, mini_batch=mini_batch,
-                validation_pct=validation_pct, device=device,
-                early_stop_patience=int(early_stop_patience), compile_mode=compile_mode,
-                precision=precision, engine=engine, comm=comm, seed=seed, streaming=streaming,
-                time_window=time_window, sampling=sampling,
-            )
+        def make_task(resume_now):
+            def task(i, x, blob=blob):
+                return handle_model(
+                    i, x, torch_obj=blob, iters=iters, verbose=verbose, mini_batch=mini_batch,
+                    validation_pct=validation_pct, device=device,
+                    early_stop_patience=int(early_stop_patience), compile_mode=compile_mode,
+                    precision=precision, engine=engine, comm=comm, seed=seed, streaming=streaming,
+                    time_window=time_window, sampling=sampling, checkpoint_dir=checkpoint_dir,
+                    checkpoint_every=checkpoint_every, resume=resume_now,
+                )
 
-        task._accepts_blocks = True
-        out = mapPartitionsWithIndex(rdd, task).collect()
+            task._accepts_blocks = True
+            return task
+
+        # Barrier-stage semantics: one failed task fails the whole stage; the stage is retried as a
+        # whole (like Spark does) and, when checkpointing is on, resumes from the last checkpoint.
+        out = None
+        for attempt in range(max_stage_retries + 1):
+            try:
+                out = mapPartitionsWithIndex(rdd, make_task(resume or attempt > 0)).collect()
+                break
+            except RuntimeError:
+                if attempt == max_stage_retries or not checkpoint_dir:
+                    raise
         state_dict, history = out[0]["state_dict"], out[0]["history"]
         if partition_shuffles - r > 1:
             rdd = rdd.repartition(rdd.getNumPartitions())

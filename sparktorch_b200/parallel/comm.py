@@ -84,6 +84,23 @@ class LocalComm:
     def finish(self) -> None:
         pass
 
+    # -- checkpoint ------------------------------------------------------------------
+    def export_state(self):
+        out = {"step_count": self.step_count, "state": {k: v.detach().cpu() for k, v in self.state.items()},
+               "es": self.es.state_vector() if self.es is not None else None}
+        if self.user_optimizer is not None:
+            out["user_optimizer"] = self.user_optimizer.state_dict()
+        return out
+
+    def import_state(self, saved) -> None:
+        self.step_count = int(saved["step_count"])
+        for k, v in saved["state"].items():
+            self.state[k].copy_(v.to(self.state[k].device))
+        if self.es is not None and saved.get("es") is not None:
+            self.es.load_state_vector(saved["es"])
+        if self.user_optimizer is not None and "user_optimizer" in saved:
+            self.user_optimizer.load_state_dict(saved["user_optimizer"])
+
 
 class CollectiveComm(LocalComm):
     def __init__(self, arena: FlatArena, spec: OptSpec, user_optimizer=None, patience: int = -1):

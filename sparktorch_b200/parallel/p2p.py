@@ -185,3 +185,20 @@ class P2PFusedComm:
 
     def finish(self) -> None:
         torch.cuda.synchronize(self.fu.device)
+
+    # -- checkpoint: optimizer shard + device-side step state ------------------------------------
+    def export_state(self):
+        fu = self.fu
+        return {"m": None if fu.m is None else fu.m.cpu(), "v": None if fu.v is None else fu.v.cpu(),
+                "state": fu.state.cpu(), "loss_hist": fu.loss_hist.cpu(), "step_count": self.step_count}
+
+    def import_state(self, saved) -> None:
+        fu = self.fu
+        if fu.m is not None and saved["m"] is not None:
+            fu.m.copy_(saved["m"].to(fu.device))
+        if fu.v is not None and saved["v"] is not None:
+            fu.v.copy_(saved["v"].to(fu.device))
+        st = saved["state"].to(fu.device)
+        fu.state[2:].copy_(st[2:])          # keep this run's barrier epoch, restore step/iter/early-stop record
+        fu.loss_hist.copy_(saved["loss_hist"].to(fu.device))
+        self.step_count = int(saved["step_count"])

@@ -51,6 +51,9 @@ class TrainConfig:
     streaming: bool = False       # keep the partition in pinned host memory, H2D one batch per step
     time_window: Optional[Tuple[int, int]] = None   # (first_step, n_steps): device-time this window (bench/profiling)
     sampling: str = "random"      # random: fresh sample w/o replacement per step | sweep: walk the shuffled partition
+    checkpoint_dir: Optional[str] = None   # every rank writes <dir>/rank<r>.pt
+    checkpoint_every: int = 0              # iterations between checkpoints (0: off)
+    resume: bool = False                   # continue from the checkpoint in checkpoint_dir if there is one
 
 
 @dataclasses.dataclass
@@ -172,6 +175,25 @@ class DeviceSampler:
         return torch.randperm(self.n, device=self.device, generator=self.gen)[: self.batch]
 
 
+def _maybe_inject_fault(cfg: "TrainConfig", rank: int, it: int) -> None:
+    """Test hook: SPARKTORCH_FAULT_INJECT='<rank>:<iter>' kills that task once (a marker file in the
+    checkpoint directory prevents re-triggering after the stage is retried)."""
+    import os
+
+    spec = os.environ.get("SPARKTORCH_FAULT_INJECT")
+    if not spec:
+        return
+    r, _, k = spec.partition(":")
+    if int(r) != rank or int(k) != it:
+        return
+    marker = os.path.join(cfg.checkpoint_dir or "/tmp", f".fault_{r}_{k}")
+    if os.path.exists(marker):
+        return
+    os.makedirs(os.path.dirname(marker), exist_ok=True)
+    open(marker, "w").close()
+    raise RuntimeError(f"injected fault on rank {rank} at iteration {it}")
+
+
 def build_comm_and_arena(model: nn.Module, opt_cls, opt_params, cfg: TrainConfig, world: int, rank: int,
                          device: torch.device):
     """Pick the gradient-exchange back-end and lay the model out in its arena."""
@@ -273,14 +295,28 @@ def train_partition(
     window = WindowTimer(cfg.time_window, device, world)
     host_loss = torch.zeros(max(cfg.iters, 1), dtype=torch.float32).pin_memory() if stream_host else None
     h2d_bytes = d2h_bytes = 0
+    from sparktorch_b200.utils import checkpoint as ckpt
+    from sparktorch_b200.utils.tracing import PhaseTimer, trace_path
+
+    tracer = PhaseTimer(device, enabled=trace_path(rank) is not None)
     has_es = cfg.early_stop_patience > 0
     need_loss = bool(cfg.verbose) or has_es
     losses: List[float] = []
     loss_buf = torch.zeros(max(cfg.iters, 1), dtype=torch.float32, device=device)
+    start_iter = 0
+    if cfg.resume and cfg.checkpoint_dir:
+        saved = ckpt.load(cfg.checkpoint_dir, rank)
+        if saved is not None and saved.get("numel") == arena.numel:
+            with torch.no_grad():
+                arena.flat_p.copy_(saved["flat_p"].to(device))
+            comm.import_state(saved["comm"])
+            start_iter = int(saved["iters_done"])
+            loss_buf[:start_iter] = torch.tensor(saved["losses"][:start_iter], device=device)
     stopped_at = None
     t_loop = time.time()
 
-    for i in range(cfg.iters):
+    for i in range(start_iter, cfg.iters):
+        _maybe_inject_fault(cfg, rank, i)
         window.before_step(i)
         if stream_host:
             # sequential sweep over the (already shuffled) pinned partition
@@ -295,12 +331,14 @@ def train_partition(
                 yb = xb
         else:
             xb, yb = x_all, y_all
-        loss = step.run(xb, yb)
+        with tracer.phase("forward_backward"):
+            loss = step.run(xb, yb)
         val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
         # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
         arena.tail[0] = val_loss if val_loss is not None else loss
         loss_buf[i] = loss
-        res = comm.reduce_and_update(need_loss)
+        with tracer.phase("exchange_update"):
+            res = comm.reduce_and_update(need_loss)
         if host_loss is not None:     # per-step device→host read of the step result
             host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
             d2h_bytes = 4
@@ -312,7 +350,14 @@ def train_partition(
         if res.stop:
             stopped_at = i
             break
+        if cfg.checkpoint_dir and cfg.checkpoint_every > 0 and (i + 1) % cfg.checkpoint_every == 0:
+            comm.finish()
+            ckpt.save(cfg.checkpoint_dir, rank, {
+                "numel": arena.numel, "flat_p": arena.flat_p.detach().cpu(), "comm": comm.export_state(),
+                "iters_done": i + 1, "losses": loss_buf[: i + 1].detach().cpu().tolist()})
     comm.finish()
+    if tracer.enabled:
+        tracer.dump_chrome_trace(trace_path(rank), rank)
     n_done = cfg.iters if stopped_at is None else stopped_at + 1
     losses = loss_buf[:n_done].detach().cpu().tolist()
     comm.average_buffers(model)
@@ -330,6 +375,8 @@ def train_partition(
         "h2d_bytes_per_step": h2d_bytes,
         "d2h_bytes_per_step": d2h_bytes,
         "streaming": bool(stream_host),
+        "resumed_from": start_iter,
+        "phases_ms": tracer.summary() if tracer.enabled else None,
         "total_seconds": t_end - t_start,
     }
     state = arena.detach_state_dict() if rank == 0 else None

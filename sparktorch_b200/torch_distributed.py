@@ -206,26 +206,31 @@ class SparkTorch(Estimator, HasInputCol, HasPredictionCol, HasLabelCol, PysparkR
     engine = Param(Params._dummy(), "engine", "auto|eager|fused", typeConverter=TypeConverters.toString)
     seed = Param(Params._dummy(), "seed", "sampling seed (<0: nondeterministic)", typeConverter=TypeConverters.toInt)
     streaming = Param(Params._dummy(), "streaming", "stream batches from pinned host memory", typeConverter=TypeConverters.toBoolean)
+    checkpointDir = Param(Params._dummy(), "checkpointDir", "directory for mid-training checkpoints", typeConverter=TypeConverters.toString)
+    checkpointEvery = Param(Params._dummy(), "checkpointEvery", "iterations between checkpoints (0: off)", typeConverter=TypeConverters.toInt)
+    resume = Param(Params._dummy(), "resume", "continue from the checkpoint in checkpointDir", typeConverter=TypeConverters.toBoolean)
     sampling = Param(Params._dummy(), "sampling", "random (fresh sample per step) | sweep (walk the shuffled partition)", typeConverter=TypeConverters.toString)
 
     @keyword_only
     def __init__(self, inputCol=None, labelCol=None, torchObj=None, iters=None, predictionCol=None, partitions=None,
                  acquireLock=None, verbose=None, partitionShuffles=None, port=None, useBarrier=None, useVectorOut=None,
                  earlyStopPatience=None, miniBatch=None, validationPct=None, mode=None, device=None, compileMode=None,
-                 precision=None, engine=None, seed=None, streaming=None, sampling=None):
+                 precision=None, engine=None, seed=None, streaming=None, sampling=None, checkpointDir=None,
+                 checkpointEvery=None, resume=None):
         super().__init__()
         self._setDefault(inputCol="features", labelCol=None, torchObj="", iters=10, predictionCol="predicted",
                          partitions=-1, acquireLock=True, verbose=0, partitionShuffles=1, port=3000, useBarrier=False,
                          useVectorOut=False, earlyStopPatience=-1, miniBatch=-1, validationPct=0.0,
                          mode="synchronous", device="cpu", compileMode=None, precision="auto", engine="auto",
-                         seed=-1, streaming=False, sampling="random")
+                         seed=-1, streaming=False, sampling="random", checkpointDir=None, checkpointEvery=0, resume=False)
         self.setParams(**self._input_kwargs)
 
     @keyword_only
     def setParams(self, inputCol=None, labelCol=None, torchObj=None, iters=None, predictionCol=None, partitions=None,
                   acquireLock=None, verbose=None, partitionShuffles=None, port=None, useBarrier=None, useVectorOut=None,
                   earlyStopPatience=None, miniBatch=None, validationPct=None, mode=None, device=None, compileMode=None,
-                  precision=None, engine=None, seed=None, streaming=None, sampling=None):
+                  precision=None, engine=None, seed=None, streaming=None, sampling=None, checkpointDir=None,
+                  checkpointEvery=None, resume=None):
         return self._set(**self._input_kwargs)
 
     # getters (names as in the reference, incl. the historical misspelling)
@@ -268,7 +273,9 @@ class SparkTorch(Estimator, HasInputCol, HasPredictionCol, HasLabelCol, PysparkR
                 verbose=self.getVerbose(), mini_batch=self.getMiniBatch(), validation_pct=self.getValidationPct(),
                 device=device, early_stop_patience=self.getEarlyStopPatience(), compile_mode=self.getCompileMode(),
                 precision=precision, engine=engine, seed=seed, streaming=streaming, return_history=True,
-                time_window=getattr(self, "_time_window", None), sampling=_param_or(self, "sampling", "random"))
+                time_window=getattr(self, "_time_window", None), sampling=_param_or(self, "sampling", "random"),
+                checkpoint_dir=_param_or(self, "checkpointDir", None), checkpoint_every=_param_or(self, "checkpointEvery", 0),
+                resume=_param_or(self, "resume", False))
         elif mode == "hogwild" and str(device).startswith("cuda"):
             from sparktorch_b200.hogwild import train_gpu
 

@@ -1,0 +1,76 @@
+"""Auxiliary subsystems the reference lacks: checkpoint/resume, failure
+handling (barrier-stage retry), tracing, metrics."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import sparktorch_b200  # noqa: F401
+from sparktorch_b200 import SparkTorch, serialize_torch_obj
+from sparktorch_b200.runtime.engine import TrainConfig, train_partition
+from sparktorch_b200.utils import metrics
+from tests.nets import Regressor
+
+
+def _xy(n=200, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, 10)).astype(np.float32)
+    Y = (X[:, :1] - 0.5 * X[:, 1:2]).astype(np.float32)
+    return X, Y
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    X, Y = _xy()
+    torch.manual_seed(0)
+    net = Regressor()
+    import copy
+
+    dev = torch.device("cpu")
+    full = train_partition(0, 1, copy.deepcopy(net), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, Y,
+                           TrainConfig(iters=20, seed=1), dev)
+    d = str(tmp_path / "ck")
+    part = train_partition(0, 1, copy.deepcopy(net), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, Y,
+                           TrainConfig(iters=12, seed=1, checkpoint_dir=d, checkpoint_every=6), dev)
+    assert os.path.exists(os.path.join(d, "rank0.pt")) and part.history["iters_run"] == 12
+    rest = train_partition(0, 1, copy.deepcopy(net), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, Y,
+                           TrainConfig(iters=20, seed=1, checkpoint_dir=d, checkpoint_every=6, resume=True), dev)
+    assert rest.history["resumed_from"] == 12
+    np.testing.assert_allclose(rest.history["train_loss"], full.history["train_loss"], rtol=0, atol=0)
+    for k in full.state_dict:
+        assert torch.equal(rest.state_dict[k], full.state_dict[k])
+
+
+def test_barrier_stage_is_retried_and_resumes_after_a_task_failure(tmp_path, spark, monkeypatch):
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(80, 10))
+    y = (X[:, 0] > 0).astype(np.float64)
+    df = spark.createDataFrame({"label": y, "features": X}, numPartitions=2)
+    obj = serialize_torch_obj(Regressor(), nn.MSELoss(), torch.optim.Adam, lr=0.01)
+    d = str(tmp_path / "ck")
+    monkeypatch.setenv("SPARKTORCH_FAULT_INJECT", "1:7")      # executor rank 1 dies at iteration 7, once
+    est = SparkTorch(inputCol="features", labelCol="label", predictionCol="p", torchObj=obj, iters=12, seed=3,
+                     checkpointDir=d, checkpointEvery=5)
+    # the executor process inherits the env at spawn time; make sure a fresh pool sees it
+    spark.sparkContext._cluster.shutdown()
+    spark.sparkContext._cluster.__init__(2)
+    stm = est.fit(df)
+    h = stm.getTrainingHistory()
+    assert h["resumed_from"] == 5 and h["iters_run"] == 12 and len(h["train_loss"]) == 12
+    assert os.path.exists(os.path.join(d, ".fault_1_7"))
+
+
+def test_tracing_and_metrics(tmp_path, monkeypatch):
+    X, Y = _xy()
+    monkeypatch.setenv("SPARKTORCH_TRACE", str(tmp_path / "trace.json"))
+    res = train_partition(0, 1, Regressor(), nn.MSELoss(), torch.optim.SGD, {"lr": 0.05}, X, Y,
+                          TrainConfig(iters=5, seed=0), torch.device("cpu"))
+    tr = json.load(open(tmp_path / "trace.rank0.json"))
+    names = {e["name"] for e in tr["traceEvents"]}
+    assert {"forward_backward", "exchange_update"} <= names
+    assert res.history["phases_ms"]["forward_backward"]["count"] == 5
+    text = metrics.to_prometheus(res.history)
+    assert "sparktorch_iterations_total" in text and metrics.throughput(res.history) > 0
+    assert len(metrics.to_jsonl(res.history).splitlines()) == 6

@@ -106,7 +106,9 @@ def test_fused_early_stop_in_band_and_validation():
     rng = np.random.default_rng(3)
     X = rng.normal(size=(300, 10)).astype(np.float32)
     Y = rng.normal(size=(300, 1)).astype(np.float32)
-    res = _fit(Regressor(), nn.MSELoss(), torch.optim.SGD, {"lr": 0.0}, X, Y, iters=50, engine="fused", early_stop_patience=3)
+    # gradient ASCENT: the loss grows every step, so patience 3 must trip at iteration 3 (0 seeds, 1-3 are bad)
+    res = _fit(Regressor(), nn.MSELoss(), torch.optim.SGD, {"lr": 0.05, "maximize": True}, X, Y, iters=50, engine="fused",
+               early_stop_patience=3)
     assert res.history["stopped_at"] == 3 and res.history["iters_run"] == 4
     res = _fit(Regressor(), nn.MSELoss(), torch.optim.Adam, {"lr": 1e-2}, X, Y, iters=30, engine="fused",
                early_stop_patience=100, validation_pct=0.25, mini_batch=64)
@@ -136,7 +138,7 @@ def test_eager_engine_uses_fused_update_kernel_on_gpu():
     rng = np.random.default_rng(4)
     X = rng.random((256, 784)).astype(np.float32)
     Y = rng.integers(0, 10, size=(256, 1)).astype(np.float32)
-    res = _fit(MnistCNN(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=12, mini_batch=64)
+    res = _fit(MnistCNN(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=12, mini_batch=64, engine="eager")
     assert res.history["engine"] == "eager" and res.history["comm"] == "P2PFusedComm"
     assert res.history["train_loss"][-1] < res.history["train_loss"][0] * 1.5 and np.isfinite(res.history["train_loss"]).all()
 

@@ -467,3 +467,43 @@ def test_maxpool_dropout_kernels(C):
     ref2 = ref.detach().permute(0, 2, 3, 1).reshape(B, PH * PW, Cc) * 2.0
     torch.testing.assert_close(y2.float().view(B, PH * PW, Cc)[kept.unsqueeze(1).expand(-1, PH * PW, -1)],
                                ref2[kept.unsqueeze(1).expand(-1, PH * PW, -1)], rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_k_ag_gathers_weights_from_sharded_fp32_arena(C):
+    """K-AG on one GPU: the flat fp32 arena is 'owned' in 4 shards (4 separate buffers standing in for 4 GPUs);
+    the GEMM gathers + casts the weight tile itself, adds the gathered bias and fills the local bf16 copy."""
+    world, Bt, I, O = 4, 256, 784, 256
+    numel = ((O * I + 63) // 64) * 64 + 256
+    shard = ((numel // 4 + world - 1) // world) * 4
+    flat = torch.randn(numel, device=dev()) * 0.05
+    # every "owner" holds a full-size buffer but only its shard is valid (others poisoned)
+    owners = []
+    for r in range(world):
+        b = torch.full((numel,), float("nan"), device=dev())
+        b[r * shard:(r + 1) * shard] = flat[r * shard:(r + 1) * shard]
+        owners.append(b)
+    w_off, b_off = 0, ((O * I + 63) // 64) * 64
+    W = flat[w_off:w_off + O * I].view(O, I)
+    bias = flat[b_off:b_off + O]
+    x = _mk(Bt, I, 0.2, 60)
+    y = torch.zeros(Bt, O, dtype=torch.bfloat16, device=dev())
+    wb = torch.zeros(O, I, dtype=torch.bfloat16, device=dev())
+    C.gemm_bf16(x, False, wb, False, Bt, O, I, relu=True, out_bf16=y, peer_ptrs=[o.data_ptr() for o in owners],
+                peer_shard_elems=shard, peer_w_off=w_off, peer_bias_off=b_off, peer_fill_local=True)
+    ref = torch.relu(x.float() @ W.to(torch.bfloat16).float().t() + bias)
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(wb.float(), W.to(torch.bfloat16).float(), rtol=0, atol=0)
+    # small head with ragged K and fused CE
+    O2, I2 = 10, 250
+    flat2 = torch.randn(4096, device=dev()) * 0.1
+    sh2 = 1024
+    owners2 = [flat2.clone() for _ in range(4)]
+    a = _mk(Bt, I2, 0.3, 61)
+    labels = torch.randint(0, O2, (Bt,), device=dev(), dtype=torch.int32)
+    loss = torch.zeros(1, device=dev())
+    wb2 = torch.zeros(O2, 256, dtype=torch.bfloat16, device=dev())[:, :I2]
+    C.gemm_bf16(a, False, wb2, False, Bt, O2, I2, loss_kind=1, labels=labels, loss_slot=loss, loss_scale=1.0 / Bt,
+                peer_ptrs=[o.data_ptr() for o in owners2], peer_shard_elems=sh2, peer_w_off=64, peer_bias_off=3008)
+    W2 = flat2[64:64 + O2 * I2].view(O2, I2).to(torch.bfloat16).float()
+    ref2 = torch.nn.functional.cross_entropy(a.float() @ W2.t() + flat2[3008:3008 + O2], labels.long())
+    torch.testing.assert_close(loss[0], ref2, rtol=1e-3, atol=1e-3)
