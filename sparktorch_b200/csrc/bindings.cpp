@@ -239,8 +239,9 @@ class HogwildWorker {
                 std::vector<int64_t> v_ptrs, std::vector<int64_t> ctrl_ptrs, const Tensor& local_param, const Tensor& local_grad,
                 const Tensor& loss_in, bool use_val_loss, int64_t numel, bool acquire_lock, int64_t kind, double lr, double beta1,
                 double beta2, double eps, double weight_decay, double momentum, double dampening, bool nesterov, bool maximize,
-                int64_t patience, int64_t window_len, int64_t host_mailbox_ptr)
-      : lp_(local_param), lg_(local_grad), li_(loss_in) {
+                int64_t patience, int64_t window_len, int64_t host_mailbox_ptr, const OptT& local_state, const OptT& loss_hist,
+                bool clear_after_push)
+      : lp_(local_param), lg_(local_grad), li_(loss_in), ls_(local_state), lh_(loss_hist) {
     a_ = st::HogwildArgs{};
     a_.world = int(world); a_.rank = int(rank); a_.stripes = int(stripes);
     for (int r = 0; r < world; ++r) {
@@ -256,13 +257,22 @@ class HogwildWorker {
     a_.weight_decay = float(weight_decay); a_.momentum = float(momentum); a_.dampening = float(dampening);
     a_.nesterov = nesterov; a_.maximize = maximize; a_.patience = int(patience); a_.window_len = int(window_len);
     a_.host_mailbox = reinterpret_cast<volatile uint32_t*>(host_mailbox_ptr);
+    a_.local_state = local_state ? reinterpret_cast<st::StepState*>(local_state->data_ptr()) : nullptr;
+    a_.loss_hist = loss_hist ? loss_hist->data_ptr<float>() : nullptr;
+    a_.max_iters = loss_hist ? loss_hist->numel() : 0;
+    a_.loss_slot_rw = clear_after_push ? loss_in.data_ptr<float>() : nullptr;
+    a_.local_grad_rw = clear_after_push ? local_grad.data_ptr<float>() : nullptr;
+    a_.dry_run = 0;
   }
   void pull() { check(st::hogwild_pull(a_, cur_stream()), "hogwild_pull"); }
   void push() { check(st::hogwild_push(a_, cur_stream()), "hogwild_push"); }
+  void step() { push(); }
+  void warm() { a_.dry_run = 1; push(); a_.dry_run = 0; }
 
  private:
   st::HogwildArgs a_;
   Tensor lp_, lg_, li_;
+  OptT ls_, lh_;
 };
 int64_t hw_ctrl_words() { return st::HW_CTRL_WORDS; }
 int64_t hw_max_stripes() { return st::HW_MAX_STRIPES; }
@@ -413,9 +423,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<HogwildWorker>(m, "HogwildWorker")
       .def(py::init<int64_t, int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,
                     std::vector<int64_t>, const Tensor&, const Tensor&, const Tensor&, bool, int64_t, bool, int64_t, double,
-                    double, double, double, double, double, double, bool, bool, int64_t, int64_t, int64_t>())
+                    double, double, double, double, double, double, bool, bool, int64_t, int64_t, int64_t, const OptT&,
+                    const OptT&, bool>())
       .def("pull", &HogwildWorker::pull)
-      .def("push", &HogwildWorker::push);
+      .def("push", &HogwildWorker::push)
+      .def("step", &HogwildWorker::step)
+      .def("warm", &HogwildWorker::warm);
   py::class_<GraphRunner>(m, "GraphRunner")
       .def(py::init<>())
       .def("begin_capture", &GraphRunner::begin_capture)

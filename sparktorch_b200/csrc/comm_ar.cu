@@ -40,12 +40,21 @@ ST_DEVINL int flag_index(int phase, int src_rank, int block) { return (phase * 8
 // Block-level barrier across GPUs.  Caller guarantees all threads of the block
 // reach it.  Data written before it (by any thread of the block, to any GPU) is
 // visible to peer blocks that pass the same barrier.
+template <bool RELEASE>
 ST_DEVINL void block_barrier_all_gpus(uint32_t* const* flags, int world, int rank, int phase, uint32_t epoch) {
   __syncthreads();
   const int t = threadIdx.x;
   if (t < world && t != rank) {
-    __threadfence_system();
-    st_release_sys_u32(flags[t] + flag_index(phase, rank, blockIdx.x), epoch);
+    uint32_t* theirs = flags[t] + flag_index(phase, rank, blockIdx.x);
+    if (RELEASE) {
+      // everything this block stored (to any GPU) happens-before the flag: bar.sync made it visible to
+      // this thread, st.release.sys orders it before the flag for system-scope observers (one MEMBAR.SYS)
+      st_release_sys_u32(theirs, epoch);
+    } else {
+      // nothing written by THIS kernel needs to be published (the gradients were completed by earlier
+      // kernels of the stream and are already performed at device scope): a plain system-scope store
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    }
     const uint32_t* mine = flags[rank] + flag_index(phase, t, blockIdx.x);
     while (int32_t(ld_acquire_sys_u32(mine) - epoch) < 0) {
     }
@@ -117,7 +126,32 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
   __syncthreads();
   const uint32_t epoch = s_epoch;
 
-  if (MODE == 0 && W > 1) block_barrier_all_gpus(a.flags, W, me, 0, epoch);
+  if (MODE == 0 && W > 1) block_barrier_all_gpus<false>(a.flags, W, me, 0, epoch);
+
+  // ---- owned shard (in float4 units; the arena is a multiple of 64 elements)
+  const int64_t n4 = a.numel >> 2;
+  int64_t lo4 = 0, hi4 = n4;
+  if (MODE == 0 && W > 1) {
+    const int64_t per = (n4 + W - 1) / W;
+    lo4 = per * me;
+    hi4 = lo4 + per < n4 ? lo4 + per : n4;
+    if (lo4 > n4) lo4 = n4;
+  }
+  // Issue the first gradient loads (NVLink round trip ~2 us) BEFORE the early-stop decision below, so the
+  // latency of the peer loads overlaps the tail-slot loads and the block-wide sync of that decision.
+  const int64_t i4_first = lo4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  float4 g_first = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE == 0 && i4_first < hi4) {
+    if (a.mc_grad != nullptr && W > 1) {
+      g_first = ld_reduce_mc_f4(a.mc_grad + (i4_first << 2));
+    } else {
+      g_first = reinterpret_cast<const float4*>(a.grad[me])[i4_first];
+      for (int r = 1; r < W; ++r) {
+        const float4 q = ld_f4_stream(reinterpret_cast<const float4*>(a.grad[(me + r) % W]) + i4_first);
+        g_first.x += q.x; g_first.y += q.y; g_first.z += q.z; g_first.w += q.w;
+      }
+    }
+  }
 
   // ---- loss + early stopping: every block of every rank computes the same decision
   if (MODE == 0 && threadIdx.x == 0) {
@@ -149,15 +183,6 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
   __syncthreads();
   const bool skip_update = (MODE == 0) && (s_stop != 0);
 
-  // ---- owned shard (in float4 units; the arena is a multiple of 64 elements)
-  const int64_t n4 = a.numel >> 2;
-  int64_t lo4 = 0, hi4 = n4;
-  if (MODE == 0 && W > 1) {
-    const int64_t per = (n4 + W - 1) / W;
-    lo4 = per * me;
-    hi4 = lo4 + per < n4 ? lo4 + per : n4;
-    if (lo4 > n4) lo4 = n4;
-  }
   __shared__ OptConsts s_oc;
   __shared__ long long s_step1;
   if (threadIdx.x == 32 || (blockDim.x <= 32 && threadIdx.x == 0)) {   // one thread per block pays for the powf
@@ -182,7 +207,9 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
       float4 p = reinterpret_cast<const float4*>(a.param[me])[i4];
       if (MODE == 0) {
         float4 g;
-        if (a.mc_grad != nullptr && W > 1) {
+        if (i4 == i4_first) {
+          g = g_first;
+        } else if (a.mc_grad != nullptr && W > 1) {
           g = ld_reduce_mc_f4(a.mc_grad + e);
         } else {
           g = reinterpret_cast<const float4*>(a.grad[me])[i4];
@@ -242,7 +269,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
     }
   }
 
-  if (MODE == 0 && W > 1) block_barrier_all_gpus(a.flags, W, me, 1, epoch);
+  if (MODE == 0 && W > 1) block_barrier_all_gpus<true>(a.flags, W, me, 1, epoch);
 
   if (MODE == 0 && a.zero_grads) {
     // Clear the local gradient arena for the next step.  Block b may only clear what
@@ -332,7 +359,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_sum_kernel(const SumArgs
   __syncthreads();
   const uint32_t epoch = s_epoch;
   const int W = a.world, me = a.rank;
-  block_barrier_all_gpus(a.flags, W, me, 0, epoch);
+  block_barrier_all_gpus<false>(a.flags, W, me, 0, epoch);
   const int64_t n4 = a.n >> 2;
   const int64_t per = (n4 + W - 1) / W;
   const int64_t lo4 = per * me < n4 ? per * me : n4;
@@ -356,7 +383,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_sum_kernel(const SumArgs
       for (int r = 0; r < W; ++r) reinterpret_cast<float4*>(a.bufs[(me + r) % W])[i4] = g;
     }
   }
-  block_barrier_all_gpus(a.flags, W, me, 1, epoch);
+  block_barrier_all_gpus<true>(a.flags, W, me, 1, epoch);
   if (threadIdx.x == 0) {
     __threadfence();
     s_last = (atomicAdd(&a.state->blocks_done, 1u) == gridDim.x - 1);

@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(HW_THREADS) hw_pull_kernel(const HogwildArgs a
 }
 
 __global__ void __launch_bounds__(HW_THREADS) hw_push_kernel(const HogwildArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (a.dry_run) return;
   const int r = (a.rank + blockIdx.y) % a.world;
   const int s = blockIdx.x;
   const StripeRange rg = stripe_range(a.numel, a.world, gridDim.x, r, s);
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_push_kernel(const HogwildArgs a
     P[i] = p;
     if (has_m) Mv[i] = m;
     if (a.kind != 0) Vv[i] = v;
+    if (a.local_grad_rw != nullptr) reinterpret_cast<float4*>(a.local_grad_rw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (a.acquire_lock) stripe_unlock(lock);
 
@@ -173,9 +177,19 @@ __global__ void __launch_bounds__(HW_THREADS) hw_push_kernel(const HogwildArgs a
         st_release_sys_u32(c0 + HW_CTRL_ES_LOCK, 0u);
       }
     }
+    const float train_loss = a.loss_in[0];
+    int64_t it = 0;
+    if (a.local_state != nullptr) {
+      it = a.local_state->iter;
+      a.local_state->iter = it + 1;
+      a.local_state->step = it + 1;
+    }
+    if (a.loss_hist != nullptr && it < a.max_iters) a.loss_hist[it] = train_loss;
+    if (a.loss_slot_rw != nullptr) { a.loss_slot_rw[0] = 0.f; a.loss_slot_rw[1] = 0.f; }
     if (a.host_mailbox != nullptr) {
+      a.host_mailbox[2] = __float_as_uint(train_loss);
+      a.host_mailbox[1] = uint32_t(it + 1);
       a.host_mailbox[0] = ld_acquire_sys_u32(a.ctrl[a.rank] + HW_CTRL_STOP);
-      a.host_mailbox[2] = __float_as_uint(a.loss_in[0]);
     }
   }
 }
@@ -190,8 +204,7 @@ int hogwild_pull(const HogwildArgs& a, cudaStream_t stream) {
 
 int hogwild_push(const HogwildArgs& a, cudaStream_t stream) {
   if (a.world > 8 || (a.numel & 63) || a.stripes < 1 || a.stripes > HW_MAX_STRIPES) return -1;
-  hw_push_kernel<<<hw_grid(a), HW_THREADS, 0, stream>>>(a);
-  return int(cudaGetLastError());
+  return int(launch_kernel(hw_push_kernel, hw_grid(a), dim3(HW_THREADS), 0, stream, a));
 }
 
 }  // namespace st

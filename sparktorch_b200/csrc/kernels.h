@@ -161,6 +161,12 @@ struct HogwildArgs {
   int nesterov, maximize;
   int patience, window_len;
   volatile uint32_t* host_mailbox;
+  StepState* local_state;     // optional: iteration counter of this worker (advanced by every push)
+  float* loss_hist;           // optional: [max_iters] this worker's loss per iteration
+  int64_t max_iters;
+  float* loss_slot_rw;        // optional: the loss slot is cleared after it was consumed (fused-loss epilogues red.add into it)
+  float* local_grad_rw;       // optional: clear this worker's gradient arena after it was applied
+  int dry_run;                // 1: launch only (module warm-up before graph capture)
 };
 int hogwild_pull(const HogwildArgs& a, cudaStream_t stream);
 int hogwild_push(const HogwildArgs& a, cudaStream_t stream);

@@ -188,8 +188,15 @@ def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_p
             raise RuntimeError(f"partition {index} is empty")
         cfg = TrainConfig(iters=iters, mini_batch=mini_batch, validation_pct=validation_pct,
                           early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev), seed=seed)
-        res = train_partition_hogwild(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y,
-                                      cfg, dev, acquire_lock, window_len)
+        res = None
+        if not acquire_lock:      # lock-free: the graph-captured worker with K-AG forward GEMMs
+            from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
+
+            res = train_partition_hogwild_fused(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params,
+                                                X, Y, cfg, dev, window_len)
+        if res is None:
+            res = train_partition_hogwild(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y,
+                                          cfg, dev, acquire_lock, window_len)
     finally:
         rendezvous.shutdown()
     return [{"state_dict": res.state_dict, "history": res.history}] if rank == 0 else []

@@ -83,7 +83,7 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
         blk.peer_ptrs("v") if spec.n_state >= 2 else [], blk.peer_ptrs("ctrl"), local_p, local_g, loss_in,
         x_val is not None, numel, bool(acquire_lock), spec.kind_id, spec.lr, spec.beta1, spec.beta2, spec.eps,
         spec.weight_decay, spec.momentum, spec.dampening, spec.nesterov, spec.maximize, cfg.early_stop_patience,
-        max(1, window_len), mailbox.data_ptr())
+        max(1, window_len), mailbox.data_ptr(), None, None, False)
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
@@ -135,4 +135,157 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
     state = arena.detach_state_dict() if rank == 0 else None
     if world > 1:
         dist.barrier()                             # keep peer memory alive until everyone has read it
+    return FitResult(state, history)
+
+
+# ----------------------------------------------------------------------------- fused (graph-captured) worker
+class HogwildBackend:
+    """Stands in for ``FusedUpdate`` inside :class:`FusedMLP`: parameters live sharded on their owners
+    (symmetric memory), gradients / bf16 weight copies / step counters are private to the worker."""
+
+    use_multicast = False
+
+    def __init__(self, numel, wbf16_elems, spec, world, rank, device, patience, window_len, max_iters, acquire_lock):
+        C = native.load(required=True)
+        self.C, self.numel, self.world, self.rank, self.device = C, numel, world, rank, device
+        blk = SymmBlock(device, world, rank)
+        blk.reserve("param", numel * 4)
+        if spec.n_state >= 1:
+            blk.reserve("m", numel * 4)
+        if spec.n_state >= 2:
+            blk.reserve("v", numel * 4)
+        blk.reserve("ctrl", C.hw_ctrl_words() * 4)
+        blk.rendezvous()
+        self.block = blk
+        self.owner_param = blk.view("param", torch.float32, numel)
+        self.param = torch.zeros(numel, device=device)                  # local snapshot (init + final pull)
+        self.grad = torch.zeros(numel + TAIL, device=device)
+        self.wbf16 = torch.zeros(wbf16_elems, dtype=torch.bfloat16, device=device)
+        self.state = torch.zeros(C.step_state_bytes() // 4, dtype=torch.int32, device=device)
+        self.loss_hist = torch.zeros(max(1, max_iters), device=device)
+        self.mailbox = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.loss_in = torch.zeros(2, device=device)
+        n4 = numel // 4
+        self.shard_elems = ((n4 + world - 1) // world) * 4
+        self.peer_param_ptrs = blk.peer_ptrs("param")
+        self.stripes = pick_stripes(numel, world, C.hw_max_stripes())
+        self.updater = C.HogwildWorker(
+            world, rank, self.stripes, blk.peer_ptrs("param"), blk.peer_ptrs("m") if spec.n_state >= 1 else [],
+            blk.peer_ptrs("v") if spec.n_state >= 2 else [], blk.peer_ptrs("ctrl"), self.param, self.grad, self.loss_in,
+            False, numel, bool(acquire_lock), spec.kind_id, spec.lr, spec.beta1, spec.beta2, spec.eps, spec.weight_decay,
+            spec.momentum, spec.dampening, spec.nesterov, spec.maximize, patience, max(1, window_len),
+            self.mailbox.data_ptr(), self.state, self.loss_hist, True)
+
+    def iters_done(self) -> int:
+        return int(self.mailbox[1])
+
+    def stopped(self) -> bool:
+        return bool(self.mailbox[0])
+
+    def last_loss(self) -> float:
+        return float(self.mailbox[2:3].view(torch.float32)[0])
+
+
+def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg: TrainConfig, device,
+                                  window_len: int):
+    """Lock-free hogwild for lowered MLPs: the whole worker iteration is one CUDA graph -
+    K-AG forward GEMMs (weights gathered from their owners inside the GEMM), fused loss, backward GEMMs,
+    remote-apply push - replayed by the native runner without Python or barriers.  Returns None when the
+    model does not lower (caller falls back to the eager hogwild worker)."""
+    from sparktorch_b200.runtime.fused_mlp import FusedMLP, _pad, _to_bf16_padded, loss_kind, lower_mlp
+
+    spec = parse_optimizer(opt_cls, opt_params)
+    if spec.kind == "other" or cfg.precision not in ("auto", "bf16"):
+        return None
+    lowered = lower_mlp(model)
+    kind = loss_kind(criterion, lowered) if lowered is not None else None
+    if kind is None or (Y is None and kind != "mse") or cfg.validation_pct > 0:
+        return None
+    if lowered.layers[-1].module.out_features > 32 or any(ls.module.in_features % 8 for ls in lowered.layers):
+        return None
+    C = native.load(required=True)
+    t_start = time.time()
+    torch.cuda.set_device(device)
+    if Y is None:
+        Y = X
+    n = X.shape[0]
+    use_mb = 0 < cfg.mini_batch < n
+    Bt = cfg.mini_batch if use_mb else n
+    d0 = X.shape[1]
+    model = model.to(device)
+    stream = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(stream):
+        plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, 0, cfg.early_stop_patience, cfg.iters + 1,
+                        backend_factory=lambda numel, wb: HogwildBackend(numel, wb, spec, world, rank, device,
+                                                                          cfg.early_stop_patience, window_len, cfg.iters + 1,
+                                                                          False))
+        be = plan.fu
+        if world > 1:
+            dist.broadcast(be.param, src=0)
+        be.owner_param.copy_(be.param)
+        src = _to_bf16_padded(torch.from_numpy(np.ascontiguousarray(X)), device)
+        yt = torch.from_numpy(np.ascontiguousarray(Y))
+        tgt = (yt.reshape(-1).to(torch.int32) if kind == "ce" else yt.to(torch.float32).reshape(n, -1)).to(device)
+        plan.train["acts"][0], plan.train["tgt"] = src, tgt
+        windowed = use_mb
+        if windowed:
+            plan.window = (max(1, n // Bt), Bt)
+        plan.loss_slot = be.loss_in[0:1]
+        plan.train_loss_slot = be.loss_in[0:1]
+
+        def enqueue():
+            plan.n_launch = 0
+            plan.forward(plan.train, slot=plan.loss_slot, train=True, windowed=windowed)
+            plan.backward(plan.train, windowed=windowed)
+            be.updater.step()
+            plan.n_launch += 1
+
+        # warm-up outside capture without touching the shared parameters: forward/backward + a dry push
+        plan.forward(plan.train, slot=plan.loss_slot, train=True, windowed=windowed)
+        plan.backward(plan.train, windowed=windowed)
+        be.updater.warm()
+        stream.synchronize()
+        be.grad.zero_()
+        be.loss_in.zero_()
+        if world > 1:
+            dist.barrier()
+        runner = C.GraphRunner()
+        use_pdl = True
+        for attempt in range(2):
+            C.set_pdl(use_pdl)
+            try:
+                runner.begin_capture()
+                enqueue()
+                runner.end_capture()
+                break
+            except RuntimeError:
+                C.set_pdl(False)
+                if attempt == 1:
+                    raise
+                try:
+                    runner.end_capture()
+                except RuntimeError:
+                    pass
+                runner, use_pdl = C.GraphRunner(), False
+        C.set_pdl(False)
+        t_loop = time.time()
+        runner.run(0, cfg.iters, be.mailbox.data_ptr(), 4 if cfg.early_stop_patience > 0 else 0)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        be.updater.pull()
+        stream.synchronize()
+    t_end = time.time()
+    done = be.iters_done()
+    history = {
+        "engine": "fused_mlp", "comm": "HogwildP2P+K-AG", "world_size": world, "precision": "bf16",
+        "train_loss": be.loss_hist[:done].cpu().tolist(), "stopped_at": (done - 1) if be.stopped() else None,
+        "iters_run": done, "samples_per_step": Bt, "stripes": be.stripes, "gpu_launches_per_step": plan.n_launch,
+        "pdl": use_pdl, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
+        "pushes_total": int(be.block.view("ctrl", torch.int32, C.hw_ctrl_words())[2 * C.hw_max_stripes() + 1]) if rank == 0 else None,
+    }
+    state = plan.arena.detach_state_dict() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    del _pad
     return FitResult(state, history)

@@ -55,10 +55,6 @@ class SymmBlock:
         import torch.distributed._symmetric_memory as symm
 
         group = dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
         self.buf = symm.empty(self.total, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self._handle = symm.rendezvous(self.buf, group.group_name)
@@ -114,7 +110,10 @@ class FusedUpdate:
         self.loss_hist = torch.zeros(max(1, max_iters), dtype=torch.float32, device=device)
         self.mailbox = torch.zeros(4, dtype=torch.int32).pin_memory()
         self.spec, self.patience = spec, patience
-        self.use_multicast = use_multicast and world > 1 and self.block.multicast_base != 0
+        import os
+
+        self.use_multicast = (use_multicast and world > 1 and self.block.multicast_base != 0
+                              and os.environ.get("SPARKTORCH_NVLS", "1") == "1")
         self.updater = None
         self._segs = None
 

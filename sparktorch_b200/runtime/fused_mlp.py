@@ -153,7 +153,7 @@ class FusedMLP:
     """Device buffers + enqueue functions of one replica."""
 
     def __init__(self, model: nn.Module, lowered: Lowered, kind: str, spec, world: int, rank: int,
-                 device: torch.device, batch: int, val_rows: int, patience: int, max_iters: int):
+                 device: torch.device, batch: int, val_rows: int, patience: int, max_iters: int, backend_factory=None):
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
         self.C = native.load(required=True)
@@ -170,10 +170,14 @@ class FusedMLP:
         for l in range(1, L + 1):
             w_off.append(off)
             off += _pad(d[l] * _pad(d[l - 1]), 64)
-        self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
+        if backend_factory is not None:      # hogwild: owner-sharded parameters, K-AG forward, remote-apply push
+            self.fu = backend_factory(numel, off)
+        else:
+            self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
         pos = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
         rows, self.Wb, self.bias, self.gW, self.gb = [], [], [], [], []
+        self.peer_kw = []                     # per layer: K-AG arguments of the forward GEMM (empty dict = local weights)
         seg_of = {}
         for l, ls in enumerate(lowered.layers, start=1):
             ldw = _pad(d[l - 1])
@@ -181,6 +185,7 @@ class FusedMLP:
             seg_of[wo] = [wo, d[l], d[l - 1], w_off[l - 1], ldw, -1, 0, 1]
             self.Wb.append(self.fu.wbf16[w_off[l - 1]: w_off[l - 1] + d[l] * ldw].view(d[l], ldw)[:, : d[l - 1]])
             self.gW.append(self.fu.grad[wo: wo + d[l] * d[l - 1]].view(d[l], d[l - 1]))
+            bo = -1
             if ls.module.bias is not None:
                 bo = pos[id(ls.module.bias)]
                 seg_of[bo] = [bo, 1, d[l], -1, 0, -1, 0, 1]
@@ -189,9 +194,16 @@ class FusedMLP:
             else:
                 self.bias.append(None)
                 self.gb.append(None)
+            peer = getattr(self.fu, "peer_param_ptrs", None)
+            if peer:
+                self.peer_kw.append(dict(peer_ptrs=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo,
+                                         peer_bias_off=bo, peer_fill_local=True))
+            else:
+                self.peer_kw.append({})
         for o in sorted(seg_of):
             rows.append(seg_of[o])
-        self.fu.build(rows, zero_grads=True)
+        if backend_factory is None:
+            self.fu.build(rows, zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]          # tail[0]: rides in the all-reduce
         self.train_loss_slot = self.fu.grad[numel + 2: numel + 3]  # tail[2]: local record when validating
         # ---- activations ----------------------------------------------------------
@@ -235,6 +247,11 @@ class FusedMLP:
             last = l == L
             flags = (1 if (windowed and l == 1) else 0)
             kw = dict(bias=self.bias[l - 1], relu=self.lowered.layers[l - 1].relu)
+            if self.peer_kw[l - 1] and buf is self.train:
+                # K-AG: this GEMM gathers W_l (and b_l) from the parameter owners over NVLink, casts to bf16 in
+                # flight and leaves the gathered copy in the local bf16 arena for the dgrad GEMM
+                kw["bias"] = None
+                kw.update(self.peer_kw[l - 1])
             if not last:
                 kw["out_bf16"] = acts[l]
             elif slot is not None and self.fuse_loss:
