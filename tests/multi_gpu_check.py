@@ -130,6 +130,18 @@ def main():
             assert all(torch.isfinite(v).all() for v in hw.state_dict.values())
             print(f"hogwild lock={lock} ok: pushes={hh['pushes_total']} stripes={hh['stripes']} loss {hh['train_loss'][0]:.3f}->{hh['train_loss'][-1]:.3f}", flush=True)
         dist.barrier()
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
+
+    cfg = TrainConfig(iters=200, mini_batch=256, device="cuda", seed=9, sampling="sweep")
+    hf = train_partition_hogwild_fused(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y,
+                                       cfg, dev, window_len=world)
+    assert hf is not None and hf.history["iters_run"] == 200
+    tl = hf.history["train_loss"]
+    assert np.isfinite(tl).all() and np.mean(tl[-10:]) < 0.7 * np.mean(tl[:3]), tl[::20]
+    if rank == 0:
+        assert hf.history["pushes_total"] == 200 * world
+        print(f"fused hogwild (K-AG) ok: {tl[0]:.3f}->{tl[-1]:.3f} launches/step {hf.history['gpu_launches_per_step']} "
+              f"{1e6 * hf.history['loop_seconds'] / 200:.1f} us/iter", flush=True)
     dist.barrier()
     if rank == 0:
         print("fused fit ok:", [round(v, 3) for v in h["train_loss"][::20]], "comm", h["comm"], flush=True)

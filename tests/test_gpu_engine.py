@@ -270,3 +270,28 @@ def test_fused_cnn_lenet_chain_conv_pool_conv():
     got = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=15, engine="fused")
     assert got.history["engine"] == "fused_cnn"
     np.testing.assert_allclose(got.history["train_loss"], ref.history["train_loss"], rtol=0.15, atol=0.03)
+
+
+def test_hogwild_fused_worker_matches_sync_fused_on_one_gpu():
+    """World size 1: the lock-free fused hogwild worker (K-AG forward GEMMs + remote-apply push in one CUDA
+    graph) is plain sequential Adam - same numbers as the synchronous fused engine."""
+    import copy
+
+    from sparktorch_b200.models import mnist_dnn
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
+    from sparktorch_b200.runtime.engine import TrainConfig
+
+    X, Y = _data(n=2048)
+    torch.manual_seed(2)
+    net = mnist_dnn()
+    dev = torch.device("cuda", 0)
+    cfg = TrainConfig(iters=40, mini_batch=256, device="cuda", seed=4, sampling="sweep")
+    hw = train_partition_hogwild_fused(0, 1, copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3},
+                                       X, Y, cfg, dev, window_len=1)
+    assert hw is not None and hw.history["comm"] == "HogwildP2P+K-AG" and hw.history["iters_run"] == 40
+    assert hw.history["gpu_launches_per_step"] == 9          # 3 K-AG fwd + 3 wgrad + 2 dgrad + push
+    ref = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=40, mini_batch=256, engine="fused",
+               sampling="sweep", seed=4)
+    np.testing.assert_allclose(hw.history["train_loss"], ref.history["train_loss"], rtol=2e-3, atol=2e-4)
+    for k in ref.state_dict:
+        torch.testing.assert_close(hw.state_dict[k], ref.state_dict[k], rtol=1e-2, atol=1e-4)
