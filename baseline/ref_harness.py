@@ -69,6 +69,7 @@ class TimedAdam(torch.optim.Adam):
                 self._e0 = torch.cuda.Event(enable_timing=True)
                 self._e1 = torch.cuda.Event(enable_timing=True)
             self._t0 = time.perf_counter()
+            self._host_t0 = time.time()
             if cuda:
                 self._e0.record()
         elif i == self._w + self._k:
@@ -81,6 +82,6 @@ class TimedAdam(torch.optim.Adam):
 
             rank = dist.get_rank() if dist.is_initialized() else 0
             with open(os.path.join(self._out, f"ref_timing_rank{rank}.json"), "w") as fh:
-                json.dump({"device_ms": ms, "wall_ms": wall, "steps": self._k}, fh)
+                json.dump({"device_ms": ms, "wall_ms": wall, "steps": self._k, "host_t0": self._host_t0, "host_t1": time.time()}, fh)
             self._fence()
         return super().zero_grad(set_to_none)

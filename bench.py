@@ -108,10 +108,11 @@ def run_reference(args):
     est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
                      iters=args.warmup + args.steps + 1, verbose=0, mode="synchronous", device=args.device,
                      miniBatch=-1, earlyStopPatience=-1)
-    clocks = ClockSampler(100, list(range(args.gpus))).start()
+    clocks = ClockSampler(20, list(range(args.gpus))).start()
     t0 = time.time()
     est.fit(df)
     fit_s = time.time() - t0
+    time.sleep(0.15)
     clocks.stop()
     recs = [json.load(open(f)) for f in sorted(glob.glob(os.path.join(out_dir, "ref_timing_rank*.json")))]
     if len(recs) != args.gpus:
@@ -132,7 +133,8 @@ def run_reference(args):
                    "l2": "256-row partition, cache resident (reference keeps its partition on device)"},
         "e2e": {"value": n * args.steps / (wall_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 4, "note": "wall clock over the same K iterations; data resident on device"},
-        "gpu_launches": 0, "fit_seconds": fit_s, "clocks": clocks.summary(),
+        "gpu_launches": 0, "fit_seconds": fit_s,
+        "clocks": clocks.summary(*clocks.window(min(r["host_t0"] for r in recs), max(r["host_t1"] for r in recs))),
     })
     spark.stop()
 
@@ -166,11 +168,20 @@ def run_ours(args):
         est._time_window = (args.warmup, args.steps)
         return est.fit(df).getTrainingHistory()
 
-    clocks = ClockSampler(100, list(range(args.gpus))).start()
+    clocks = ClockSampler(20, list(range(args.gpus))).start()
     h = fit(streaming=False)
-    m1 = clocks.mark()
     he = None if args.no_e2e else fit(streaming=True)
+    time.sleep(0.15)
     clocks.stop()
+
+    def clock_summary(hist):
+        w = hist["window_ms"]
+        lo, hi = clocks.window(w["host_t0"], w["host_t1"])
+        out = clocks.summary(lo, hi)
+        out["window_s"] = round(w["host_t1"] - w["host_t0"], 4)
+        out["note"] = "nvidia-smi samples (20 ms period) taken during the timed window +-0.12 s"
+        return out
+
     gb = args.batch * args.gpus
     dev_ms = h["window_ms"]["device_ms"]
     value = gb * args.steps / (dev_ms / 1e3)
@@ -186,7 +197,7 @@ def run_ours(args):
                          f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
                          "weights/optimizer state stay cache resident as in any training loop"},
         "gpu_launches": int(h.get("gpu_launches_per_step", 0) * args.steps),
-        "clocks": clocks.summary(0, m1),
+        "clocks": clock_summary(h),
     }
     if he is not None:
         e_ms = max(he["window_ms"]["device_ms"], he["window_ms"]["wall_ms"])
@@ -195,7 +206,7 @@ def run_ours(args):
                       "d2h_bytes_per_step": he.get("d2h_bytes_per_step", 0),
                       "ms_per_step": e_ms / args.steps, "engine": he.get("engine"),
                       "gpu_launches": int(he.get("gpu_launches_per_step", 0) * args.steps),
-                      "clocks": clocks.summary(m1)}
+                      "clocks": clock_summary(he)}
     emit(out)
     spark.stop()
 

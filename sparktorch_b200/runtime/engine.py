@@ -108,6 +108,7 @@ class WindowTimer:
         if self.window is not None and i == self.window[0]:
             self._sync()
             self._t0 = time.perf_counter()
+            self.host_t0 = time.time()
             if self.device.type == "cuda":
                 self.e0.record()
 
@@ -126,10 +127,14 @@ class WindowTimer:
 
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             self.ms = (float(t[0]), float(t[1]))
+            self.host_t1 = time.time()
             self._sync()
 
     def result_ms(self):
-        return None if self.ms is None else {"device_ms": self.ms[0], "wall_ms": self.ms[1]}
+        if self.ms is None:
+            return None
+        return {"device_ms": self.ms[0], "wall_ms": self.ms[1], "host_t0": getattr(self, "host_t0", None),
+                "host_t1": getattr(self, "host_t1", None)}
 
 
 class EagerStep:

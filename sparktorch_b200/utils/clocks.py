@@ -18,6 +18,7 @@ class ClockSampler:
         self.gpus = gpus
         self.proc = None
         self.lines: List[str] = []
+        self.stamps: List[float] = []
         self._thr = None
 
     def start(self) -> "ClockSampler":
@@ -31,8 +32,11 @@ class ClockSampler:
             return self
 
         def pump():
+            import time
+
             for line in self.proc.stdout:  # type: ignore[union-attr]
                 self.lines.append(line.strip())
+                self.stamps.append(time.time())
 
         self._thr = threading.Thread(target=pump, daemon=True)
         self._thr.start()
@@ -48,6 +52,13 @@ class ClockSampler:
                 self.proc.wait(timeout=3)
             except Exception:
                 self.proc.kill()
+
+    def window(self, t0: float, t1: float, margin: float = 0.12):
+        """Indices [lo, hi) of the samples taken between host times t0 and t1 (+- margin seconds)."""
+        idx = [i for i, t in enumerate(self.stamps) if t0 - margin <= t <= t1 + margin]
+        if not idx:
+            return 0, 0
+        return idx[0], idx[-1] + 1
 
     def summary(self, lo: int = 0, hi: Optional[int] = None) -> Dict:
         rows = [ln.split(", ") for ln in self.lines[lo:hi] if ln.count(",") >= 8]
