@@ -142,13 +142,19 @@ class EagerStep:
 
     name = "eager"
 
-    def __init__(self, model: nn.Module, criterion, arena: FlatArena):
+    def __init__(self, model: nn.Module, criterion, arena: FlatArena, autocast_bf16: bool = False):
         self.model, self.criterion, self.arena = model, criterion, arena
+        self.autocast_bf16 = autocast_bf16      # precision='bf16' on the eager GPU path: bf16 compute, fp32 master weights
 
     def run(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.arena.zero_grad()
-        out = self.model(x)
-        loss = self.criterion(out, y)
+        if self.autocast_bf16:
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                out = self.model(x)
+            loss = self.criterion(out.float(), y)
+        else:
+            out = self.model(x)
+            loss = self.criterion(out, y)
         loss.backward()
         return loss.detach()
 
@@ -290,7 +296,7 @@ def train_partition(
             pass
     comm, arena = build_comm_and_arena(model, opt_cls, opt_params, cfg, world, rank, device)
     comm.broadcast_params()
-    step = EagerStep(model, criterion, arena)
+    step = EagerStep(model, criterion, arena, autocast_bf16=(cfg.precision == "bf16" and device.type == "cuda"))
 
     n = x_all.shape[0]
     use_mb = 0 < cfg.mini_batch < n
