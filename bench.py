@@ -35,6 +35,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 METRIC = "MNIST-DNN samples/sec (whole job, device-timed, max over ranks)"
+METRIC_CNN = "MNIST-CNN samples/sec (whole job, device-timed, max over ranks)"
 IN_FEATURES, N_CLASSES = 784, 10
 L2_BYTES = 126 * 1024 * 1024
 
@@ -50,7 +51,16 @@ def parse_args():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--model", default="dnn", choices=["dnn", "cnn"], help="dnn: examples/simple_dnn.py, cnn: examples/simple_cnn.py")
+    ap.add_argument("--mode", default="synchronous", choices=["synchronous", "hogwild"])
+    a = ap.parse_args()
+    if a.model == "cnn" and "--batch" not in sys.argv:
+        a.batch = 128                      # the CNN example's miniBatch (examples/simple_cnn.py:45)
+    return a
+
+
+MODEL_NAME = {"dnn": "MNIST-DNN 784-256-256-10 CE Adam(lr=1e-3)",
+              "cnn": "MNIST-CNN conv5x5x16-conv3x3x32-pool2-dropout2d-fc3872x10 CE Adam(lr=1e-3)"}
 
 
 def synthetic_mnist(n_rows: int, seed: int):
@@ -102,9 +112,18 @@ def run_reference(args):
     n = args.batch * args.gpus
     x, y = synthetic_mnist(n, seed=1)
     df = spark.createDataFrame({"label": y, "features": x.astype(np.float64)}, numPartitions=args.gpus)
-    net = nn.Sequential(nn.Linear(IN_FEATURES, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, N_CLASSES))
+    if args.model == "cnn":
+        from sparktorch_b200.models.mnist import MnistCNN      # plain nn.Module definition (same net as examples/cnn_network.py)
+
+        net = MnistCNN()
+    else:
+        net = nn.Sequential(nn.Linear(IN_FEATURES, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, N_CLASSES))
     obj = serialize_torch_obj(net, nn.CrossEntropyLoss(), TimedAdam, lr=1e-3,
                               warmup=args.warmup, steps=args.steps, out_dir=out_dir)
+    if args.mode == "hogwild":
+        emit({"impl": "reference", "unavailable": "the reference's hogwild workers ignore `device` (CPU only, Flask server on the "
+              "driver; SURVEY quirk Q10) - no GPU arm exists for it; use --mode synchronous"})
+        return
     est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
                      iters=args.warmup + args.steps + 1, verbose=0, mode="synchronous", device=args.device,
                      miniBatch=-1, earlyStopPatience=-1)
@@ -122,10 +141,10 @@ def run_reference(args):
     wall_ms = max(r["wall_ms"] for r in recs)
     value = n * args.steps / (dev_ms / 1e3)
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_CNN if args.model == "cnn" else METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"model": "MNIST-DNN 784-256-256-10 CE Adam(lr=1e-3)", "global_batch": n, "seq_len": IN_FEATURES,
+        "config": {"model": MODEL_NAME[args.model], "global_batch": n, "seq_len": IN_FEATURES,
                    "parallelism": f"dp{args.gpus}", "per_gpu_batch": args.batch, "mode": "synchronous",
                    "backend": os.environ.get("SPARKTORCH_REF_BACKEND", "nccl"),
                    "note": "unmodified reference via SparkTorch.fit on sparkshim; full-batch per partition "
@@ -148,7 +167,7 @@ def run_ours(args):
 
     import sparktorch_b200  # noqa: F401
     from sparktorch_b200 import SparkTorch, serialize_torch_obj
-    from sparktorch_b200.models import mnist_dnn
+    from sparktorch_b200.models import MnistCNN, mnist_dnn
     from sparktorch_b200.utils.clocks import ClockSampler
     from pyspark.sql import SparkSession
 
@@ -158,19 +177,20 @@ def run_ours(args):
     x, y = synthetic_mnist(n, seed=1)
     df = spark.createDataFrame({"label": y, "features": x}, numPartitions=args.gpus)
     torch.manual_seed(0)
-    obj = serialize_torch_obj(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, lr=1e-3)
+    obj = serialize_torch_obj(MnistCNN() if args.model == "cnn" else mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, lr=1e-3)
     iters = args.warmup + args.steps
 
     def fit(streaming: bool):
         est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
-                         iters=iters, verbose=0, mode="synchronous", device=args.device, miniBatch=args.batch,
-                         precision="bf16", engine=args.engine, seed=0, streaming=streaming, sampling="sweep")
+                         iters=iters, verbose=0, mode=args.mode, device=args.device, miniBatch=args.batch,
+                         precision="bf16", engine=args.engine, seed=0, streaming=streaming, sampling="sweep",
+                         acquireLock=False, port=0)
         est._time_window = (args.warmup, args.steps)
         return est.fit(df).getTrainingHistory()
 
     clocks = ClockSampler(20, list(range(args.gpus))).start()
     h = fit(streaming=False)
-    he = None if args.no_e2e else fit(streaming=True)
+    he = None if (args.no_e2e or args.mode == "hogwild") else fit(streaming=True)
     time.sleep(0.15)
     clocks.stop()
 
@@ -186,12 +206,12 @@ def run_ours(args):
     dev_ms = h["window_ms"]["device_ms"]
     value = gb * args.steps / (dev_ms / 1e3)
     out = {
-        "impl": "ours", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "ours", "metric": METRIC_CNN if args.model == "cnn" else METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if h.get("precision") == "bf16" else h.get("precision", "fp32"),
         "data": "synthetic",
-        "config": {"model": "MNIST-DNN 784-256-256-10 CE Adam(lr=1e-3)", "global_batch": gb, "seq_len": IN_FEATURES,
-                   "parallelism": f"dp{args.gpus}", "per_gpu_batch": args.batch, "mode": "synchronous",
+        "config": {"model": MODEL_NAME[args.model], "global_batch": gb, "seq_len": IN_FEATURES,
+                   "parallelism": f"dp{args.gpus}", "per_gpu_batch": args.batch, "mode": args.mode,
                    "engine": h.get("engine"), "comm": h.get("comm"), "sampling": h.get("sampling"),
                    "l2": f"inputs larger than L2: resident partition {rows}x{IN_FEATURES} per GPU "
                          f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "

@@ -55,9 +55,13 @@ ST_DEVINL void block_barrier_all_gpus(uint32_t* const* flags, int world, int ran
       // kernels of the stream and are already performed at device scope): a plain system-scope store
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
     }
+    // poll with relaxed loads (no fence per iteration), one acquire fence once the flag has arrived
     const uint32_t* mine = flags[rank] + flag_index(phase, t, blockIdx.x);
-    while (int32_t(ld_acquire_sys_u32(mine) - epoch) < 0) {
-    }
+    uint32_t seen;
+    do {
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    } while (int32_t(seen - epoch) < 0);
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncthreads();
 }

@@ -168,7 +168,8 @@ def handle_model(
 
 # ------------------------------------------------------------------ GPU-resident variant
 def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_patience=-1, mini_batch=-1,
-                     validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4):
+                     validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4, time_window=None,
+                     sampling="random"):
     """Barrier-task body of ``mode='hogwild', device='cuda'``: no HTTP, the GPUs' own
     memory is the parameter server (parallel/hogwild_p2p.py)."""
     from pyspark.taskcontext import BarrierTaskContext
@@ -187,7 +188,8 @@ def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_p
         if X is None:
             raise RuntimeError(f"partition {index} is empty")
         cfg = TrainConfig(iters=iters, mini_batch=mini_batch, validation_pct=validation_pct,
-                          early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev), seed=seed)
+                          early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev), seed=seed,
+                          time_window=tuple(time_window) if time_window else None, sampling=sampling)
         res = None
         if not acquire_lock:      # lock-free: the graph-captured worker with K-AG forward GEMMs
             from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
@@ -203,7 +205,8 @@ def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_p
 
 
 def train_gpu(rdd, torch_obj, iters=10, partition_shuffles=1, verbose=1, early_stop_patience=-1, mini_batch=-1,
-              validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4):
+              validation_pct=0.0, device="cuda", seed=None, acquire_lock=True, window_len=4, time_window=None,
+              sampling="random"):
     from sparktorch_b200.distributed import _reseed_blob, mapPartitionsWithIndex
 
     blob, _ = load_base_torch(torch_obj)
@@ -212,7 +215,8 @@ def train_gpu(rdd, torch_obj, iters=10, partition_shuffles=1, verbose=1, early_s
         def task(i, x, blob=blob):
             return handle_model_gpu(i, x, blob, iters=iters, verbose=verbose, early_stop_patience=early_stop_patience,
                                     mini_batch=mini_batch, validation_pct=validation_pct, device=device, seed=seed,
-                                    acquire_lock=acquire_lock, window_len=window_len)
+                                    acquire_lock=acquire_lock, window_len=window_len, time_window=time_window,
+                                    sampling=sampling)
 
         task._accepts_blocks = True
         out = mapPartitionsWithIndex(rdd, task).collect()

@@ -198,10 +198,17 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
     if spec.kind == "other" or cfg.precision not in ("auto", "bf16"):
         return None
     lowered = lower_mlp(model)
+    is_cnn = False
+    if lowered is None:
+        from sparktorch_b200.runtime.fused_cnn import FusedCNN, lower_cnn
+
+        lowered = lower_cnn(model, X.shape[1])
+        is_cnn = lowered is not None
     kind = loss_kind(criterion, lowered) if lowered is not None else None
     if kind is None or (Y is None and kind != "mse") or cfg.validation_pct > 0:
         return None
-    if lowered.layers[-1].module.out_features > 32 or any(ls.module.in_features % 8 for ls in lowered.layers):
+    last_out = (lowered.linears if is_cnn else lowered.layers)[-1].module.out_features
+    if last_out > 32:
         return None
     C = native.load(required=True)
     t_start = time.time()
@@ -215,10 +222,14 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
     model = model.to(device)
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
-        plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, 0, cfg.early_stop_patience, cfg.iters + 1,
-                        backend_factory=lambda numel, wb: HogwildBackend(numel, wb, spec, world, rank, device,
-                                                                          cfg.early_stop_patience, window_len, cfg.iters + 1,
-                                                                          False))
+        factory = lambda numel, wb: HogwildBackend(numel, wb, spec, world, rank, device, cfg.early_stop_patience,  # noqa: E731
+                                                   window_len, cfg.iters + 1, False)
+        if is_cnn:
+            plan = FusedCNN(model, lowered, kind, spec, world, rank, device, Bt, 0, cfg.early_stop_patience, cfg.iters + 1,
+                            seed=0 if cfg.seed is None else int(cfg.seed), backend_factory=factory)
+        else:
+            plan = FusedMLP(model, lowered, kind, spec, world, rank, device, Bt, 0, cfg.early_stop_patience, cfg.iters + 1,
+                            backend_factory=factory)
         be = plan.fu
         if world > 1:
             dist.broadcast(be.param, src=0)
@@ -268,8 +279,24 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
                     pass
                 runner, use_pdl = C.GraphRunner(), False
         C.set_pdl(False)
+        from sparktorch_b200.runtime.engine import WindowTimer
+
+        window = WindowTimer(cfg.time_window, device, world)
+        check = 4 if cfg.early_stop_patience > 0 else 0
         t_loop = time.time()
-        runner.run(0, cfg.iters, be.mailbox.data_ptr(), 4 if cfg.early_stop_patience > 0 else 0)
+        segs = [(0, cfg.iters)]
+        if cfg.time_window is not None:
+            w0, wk = cfg.time_window
+            segs = [(0, w0), (w0, w0 + wk), (w0 + wk, cfg.iters)]
+        for si, (lo, hi) in enumerate(segs):
+            if hi <= lo:
+                continue
+            timed = cfg.time_window is not None and si == 1
+            if timed:
+                window.before_step(lo)
+            runner.run(lo, hi - lo, be.mailbox.data_ptr(), check)
+            if timed:
+                window.after_step(hi - 1)
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -278,7 +305,8 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
     t_end = time.time()
     done = be.iters_done()
     history = {
-        "engine": "fused_mlp", "comm": "HogwildP2P+K-AG", "world_size": world, "precision": "bf16",
+        "engine": "fused_cnn" if is_cnn else "fused_mlp", "comm": "HogwildP2P+K-AG", "world_size": world, "precision": "bf16",
+        "window_ms": window.result_ms(),
         "train_loss": be.loss_hist[:done].cpu().tolist(), "stopped_at": (done - 1) if be.stopped() else None,
         "iters_run": done, "samples_per_step": Bt, "stripes": be.stripes, "gpu_launches_per_step": plan.n_launch,
         "pdl": use_pdl, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,

@@ -189,7 +189,7 @@ class FusedCNN:
     """Buffers + enqueue functions; interface-compatible with FusedMLP."""
 
     def __init__(self, model: nn.Module, low: LoweredCNN, kind: str, spec, world: int, rank: int, device: torch.device,
-                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0):
+                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None):
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
         self.C = native.load(required=True)
@@ -225,11 +225,14 @@ class FusedCNN:
             cols = m.weight[0].numel()
             w_off[id(m)] = (off, rows, cols)
             off += _pad(rows * _pad(cols), 64)
-        self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
+        if backend_factory is not None:
+            self.fu = backend_factory(numel, off)
+        else:
+            self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
         pos = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
         seg_of = {}
-        self.Wb, self.bias, self.gW, self.gb = {}, {}, {}, {}
+        self.Wb, self.bias, self.gW, self.gb, self.peer_kw = {}, {}, {}, {}, {}
         for m in mods:
             o, rows, cols = w_off[id(m)]
             ldw = _pad(cols)
@@ -237,6 +240,7 @@ class FusedCNN:
             seg_of[wo] = [wo, rows, cols, o, ldw, -1, 0, 1]
             self.Wb[id(m)] = self.fu.wbf16[o: o + rows * ldw].view(rows, ldw)[:, :cols]
             self.gW[id(m)] = self.fu.grad[wo: wo + rows * cols].view(rows, cols)
+            bo = -1
             if m.bias is not None:
                 bo = pos[id(m.bias)]
                 seg_of[bo] = [bo, 1, rows, -1, 0, -1, 0, 1]
@@ -245,7 +249,11 @@ class FusedCNN:
             else:
                 self.bias[id(m)] = None
                 self.gb[id(m)] = None
-        self.fu.build([seg_of[o] for o in sorted(seg_of)], zero_grads=True)
+            peer = getattr(self.fu, "peer_param_ptrs", None)
+            self.peer_kw[id(m)] = dict(peer_ptrs=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo, peer_bias_off=bo,
+                                       peer_fill_local=True) if peer else {}
+        if backend_factory is None:
+            self.fu.build([seg_of[o] for o in sorted(seg_of)], zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]
         self.train_loss_slot = self.fu.grad[numel + 2: numel + 3]
         # flipped-tap weights for the dgrad GEMMs of conv 2..n
@@ -328,8 +336,11 @@ class FusedCNN:
                           g["s"], g["p"], buf["col"][i], **wkw)
             self.n_launch += 1
             M = rows * g["OH"] * g["OW"]
-            self._gemm(buf["col"][i], False, self.Wb[id(m)], False, M, g["Cout"], g["K"], bias=self.bias[id(m)], relu=cs.relu,
-                       out_bf16=buf["conv_out"][i])
+            ckw = dict(bias=self.bias[id(m)], relu=cs.relu, out_bf16=buf["conv_out"][i])
+            if self.peer_kw[id(m)] and buf is self.train:      # K-AG: conv weights gathered from their owners in the GEMM
+                ckw["bias"] = None
+                ckw.update(self.peer_kw[id(m)])
+            self._gemm(buf["col"][i], False, self.Wb[id(m)], False, M, g["Cout"], g["K"], **ckw)
             out = buf["conv_out"][i]
             ldo = out.stride(0)
             last = i == len(self.geo) - 1
@@ -352,6 +363,9 @@ class FusedCNN:
             m = ls.module
             last = l == self.L
             kw = dict(bias=self.bias[id(m)], relu=ls.relu)
+            if self.peer_kw[id(m)] and buf is self.train:
+                kw["bias"] = None
+                kw.update(self.peer_kw[id(m)])
             if not last:
                 kw["out_bf16"] = buf["lin"][l]
             elif slot is not None and self.fuse_loss:

@@ -283,7 +283,8 @@ class SparkTorch(Estimator, HasInputCol, HasPredictionCol, HasLabelCol, PysparkR
                 rdd, torch_obj, self.getIters(), self.getPartitionShuffles(), verbose=self.getVerbose(),
                 early_stop_patience=self.getEarlyStopPatience(), mini_batch=self.getMiniBatch(),
                 validation_pct=self.getValidationPct(), device=device, seed=seed,
-                acquire_lock=self.getAqcuireLock(), window_len=partitions)
+                acquire_lock=self.getAqcuireLock(), window_len=partitions, time_window=getattr(self, "_time_window", None),
+                sampling=_param_or(self, "sampling", "random"))
         elif mode == "hogwild":
             from sparktorch_b200.hogwild import get_main, train
             from sparktorch_b200.server import Server
