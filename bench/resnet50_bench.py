@@ -1,0 +1,56 @@
+"""ResNet-50 (lazy envelope, synthetic 3x224x224 rows) through SparkTorch.fit on N GPUs.
+
+Convolutions of this model still run on cuDNN via the eager engine (bf16 autocast); the gradient
+exchange + optimizer is our fused K-AR kernel (two-shot NVLink reduce-scatter + Adam + publish, 102 MB fp32
+arena).  The fp8 block-scaled tcgen05 conv path named in BASELINE.json is future work.
+
+    python bench/resnet50_bench.py --gpus 1 --steps 10 --warmup 3 [--batch 32] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node 8 ... bench/resnet50_bench.py --gpus 8
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--image", type=int, default=224)
+    a = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.nn as nn
+
+    import sparktorch_b200  # noqa: F401
+    from pyspark.sql import SparkSession
+    from sparktorch_b200 import SparkTorch, serialize_torch_obj_lazy
+    from sparktorch_b200.models import ResNet50
+
+    spark = SparkSession.builder.master(f"local[{a.gpus}]").appName("resnet50").getOrCreate()
+    n = a.batch * a.gpus
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, 3 * a.image * a.image), dtype=np.float32)
+    y = rng.integers(0, 1000, size=n).astype(np.float64)
+    df = spark.createDataFrame({"label": y, "features": x}, numPartitions=a.gpus)
+    obj = serialize_torch_obj_lazy(ResNet50, nn.CrossEntropyLoss, torch.optim.SGD, {"lr": 0.1, "momentum": 0.9},
+                                   {"num_classes": 1000, "image_size": a.image})
+    est = SparkTorch(inputCol="features", labelCol="label", predictionCol="p", torchObj=obj, iters=a.warmup + a.steps,
+                     device="cuda", precision="bf16", engine="eager", seed=0)
+    est._time_window = (a.warmup, a.steps)
+    h = est.fit(df).getTrainingHistory()
+    ms = h["window_ms"]["device_ms"]
+    print(json.dumps({"metric": "ResNet-50 samples/sec (whole job)", "value": n * a.steps / (ms / 1e3), "unit": "samples/s",
+                      "n_gpus": a.gpus, "ms_per_step": ms / a.steps, "global_batch": n, "engine": h["engine"], "comm": h["comm"],
+                      "dtype": "bf16 autocast (cuDNN convs) + fp32 master/K-AR", "data": "synthetic"}), flush=True)
+    spark.stop()
+
+
+if __name__ == "__main__":
+    main()

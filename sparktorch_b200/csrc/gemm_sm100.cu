@@ -192,7 +192,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===== K-AG producer: gather this CTA's B tiles from the parameter owners over NVLink =====
         // item = (row n, 16-byte chunk c) of a [BLOCK_N x 64] bf16 tile = 8 fp32 source values.
         constexpr int ITEMS = (BLOCK_N * 8 + 127) / 128;     // per thread per k-block (1 or 2)
-        constexpr int DEPTH = 4;                             // k-blocks of loads in flight (hides ~2 us peer latency)
+        constexpr int DEPTH = ITEMS == 1 ? 8 : 4;            // k-blocks of loads in flight (hides ~2 us peer latency)
         float4 ring[DEPTH][ITEMS][2];
         const bool k_vec = (K & 7) == 0 && (peer.w_off & 3) == 0;
         auto issue = [&](int i, float4 (&dst)[ITEMS][2]) {
