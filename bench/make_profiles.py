@@ -92,7 +92,9 @@ if os.path.exists(f"{G}/gemm_bench.json"):
     gb = json.load(open(f"{G}/gemm_bench.json"))
     with open(f"{P}/gemm_vs_cublas.md", "w") as fh:
         fh.write(f"# tcgen05 GEMM vs cuBLAS (bf16, device-timed, inputs rotated through >L2 buffers)\n\nMeasured peak (MEASURED_PEAKS.json): {peaks.get('bf16_tflops')} TFLOP/s burst.\n\n")
-        fh.write("| M | N | K | ours BN=128 TF/s | ours BN=256 TF/s | cuBLAS TF/s | best ours / measured peak |\n|---|---|---|---|---|---|---|\n")
+        fh.write("| M | N | K | ours BN=128 | ours BN=256 | persistent BN=128 | persistent BN=256 | cuBLAS | best ours / measured peak |\n|---|---|---|---|---|---|---|---|---|\n")
         for r in gb:
-            fh.write(f"| {r['M']} | {r['N']} | {r['K']} | {r['ours_bn128_tflops']:.0f} | {r['ours_bn256_tflops']:.0f} | {r['cublas_tflops']:.0f} | {r['frac_of_measured_peak']:.2f} (of measured) |\n")
+            g = lambda k: f"{r[k]:.0f}" if k in r else "-"   # noqa: E731
+            fh.write(f"| {r['M']} | {r['N']} | {r['K']} | {g('ours_bn128_tflops')} | {g('ours_bn256_tflops')} | {g('ours_bn128_persistent_tflops')} | "
+                     f"{g('ours_bn256_persistent_tflops')} | {r['cublas_tflops']:.0f} | {r['frac_of_measured_peak']:.2f} (of measured) |\n")
 print("profiles written:", sorted(os.listdir(P)))

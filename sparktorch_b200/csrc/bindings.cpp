@@ -374,6 +374,7 @@ class GraphRunner {
   uint64_t h2d_bytes_ = 0;
 };
 
+void set_persistent_mode(int64_t m) { st::g_persistent_mode = int(m); }
 void set_pdl(bool on) { st::g_use_pdl = on; }
 bool get_pdl() { return st::g_use_pdl; }
 int64_t step_state_bytes() { return int64_t(sizeof(st::StepState)); }
@@ -409,6 +410,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("pack_segments", &pack_segments);
   m.def("step_state_bytes", &step_state_bytes);
   m.def("set_pdl", &set_pdl);
+  m.def("set_persistent_mode", &set_persistent_mode);
   m.def("get_pdl", &get_pdl);
   m.def("flag_words", &flag_words);
   py::class_<Updater>(m, "Updater")

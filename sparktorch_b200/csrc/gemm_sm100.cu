@@ -24,6 +24,7 @@
 namespace st {
 
 bool g_use_pdl = false;
+int g_persistent_mode = 1;   // 0 never, 1 when tiles > #SMs, 2 always (tests)
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
@@ -40,6 +41,145 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
+
+// One 32x(CHUNK) slab of the accumulator (thread = row, registers = columns): fused epilogue math and stores.
+// Shared by the single-tile and the persistent kernel.
+template <int CHUNK>
+ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], const uint4 (&mk)[4], bool have_mask,
+                              const __nv_bfloat16* mrow, bool have_bias, const float* s_bias, int c0, int row, bool row_ok,
+                              int col0, int N, int lane, int lbl_off) {
+  const bool vec_ok = (col0 + CHUNK <= N);   // leading dims are multiples of 8 elements, col0 multiple of 16
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    float v = __uint_as_float(r[j]) * ep.alpha;
+    if (have_bias) v += s_bias[c0 + j];
+    if (ep.relu) v = fmaxf(v, 0.f);
+    acc[j] = v;
+  }
+  if (have_mask) {
+    if (row_ok && vec_ok) {
+      const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(mk);
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) acc[j] = (__bfloat162float(mb[j]) > 0.f) ? acc[j] : 0.f;
+    } else if (row_ok) {
+      for (int j = 0; j < CHUNK; ++j)
+        if (col0 + j < N) acc[j] = (__bfloat162float(mrow[col0 + j]) > 0.f) ? acc[j] : 0.f;
+    }
+  }
+  // ---- row-major fp32 of the plain result (logits for inference / validation)
+  if (ep.out_f32 != nullptr && row_ok && ep.loss_kind != 0) {
+    float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
+    for (int j = 0; j < CHUNK; ++j)
+      if (col0 + j < N) op[j] = acc[j];
+  }
+  // ---- fused loss (single n-tile, N <= CHUNK): the thread owns the whole output row.
+  //      acc[] becomes dLoss/dOutput so the stores / column sums below emit dZ and db.
+  if (ep.loss_kind == 1) {          // softmax cross entropy, mean over M rows
+    const int y = row_ok ? ep.ce_labels[row + lbl_off] : 0;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) if (j < N) mx = fmaxf(mx, acc[j]);
+    float sum = 0.f, zy = 0.f;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      if (j == y) zy = acc[j];
+      acc[j] = (j < N) ? __expf(acc[j] - mx) : 0.f;
+      sum += acc[j];
+    }
+    float li = row_ok ? (mx + __logf(sum) - zy) : 0.f;
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) acc[j] = (row_ok && j < N) ? (acc[j] * inv - (j == y ? 1.f : 0.f)) * ep.loss_scale : 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
+    if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
+  } else if (ep.loss_kind == 2) {   // mean squared error over M x N
+    float li = 0.f;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      float dlt = 0.f;
+      if (row_ok && j < N) dlt = acc[j] - ep.mse_target[size_t(row + lbl_off) * ep.ld_target + j];
+      li += dlt * dlt;
+      acc[j] = 2.f * dlt * ep.loss_scale;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
+    if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
+  }
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) acc[j] = 0.f;
+  }
+  // ---- row-major bf16
+  if (ep.out_bf16 != nullptr && row_ok) {
+    __nv_bfloat16* op = ep.out_bf16 + size_t(row) * ep.ld_out + col0;
+    if (vec_ok || (col0 + CHUNK <= ep.ld_out && ep.loss_kind != 0)) {
+      // (fused loss: the padding columns up to the pitch are written as zeros)
+#pragma unroll
+      for (int v = 0; v < CHUNK / 8; ++v) {
+        uint4 w;
+        w.x = pack_bf16x2(acc[8 * v + 0], acc[8 * v + 1]);
+        w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
+        w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]);
+        w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
+        if (col0 + 8 * v < ep.ld_out) reinterpret_cast<uint4*>(op)[v] = w;
+      }
+    } else {
+      for (int j = 0; j < CHUNK; ++j)
+        if (col0 + j < N) op[j] = __float2bfloat16(acc[j]);
+    }
+  }
+  // ---- row-major fp32 (store or red.add for split-K)
+  if (ep.out_f32 != nullptr && row_ok && ep.loss_kind == 0) {
+    float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
+    if (ep.atomic_f32) {
+      for (int j = 0; j < CHUNK; ++j)
+        if (col0 + j < N) red_add_f32(op + j, acc[j]);
+    } else if (vec_ok && (ep.ld_f32 & 3) == 0) {
+#pragma unroll
+      for (int v = 0; v < CHUNK / 4; ++v)
+        reinterpret_cast<float4*>(op)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+    } else {
+      for (int j = 0; j < CHUNK; ++j)
+        if (col0 + j < N) op[j] = acc[j];
+    }
+  }
+  // ---- transposed stores: lanes hold consecutive rows -> coalesced along m
+  if (ep.out_t_bf16 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      if (col0 + j < N && row_ok) ep.out_t_bf16[size_t(col0 + j) * ep.ld_out_t + row] = __float2bfloat16(acc[j]);
+    }
+  }
+  if (ep.out_t_f32 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      if (col0 + j < N && row_ok) {
+        float* op = ep.out_t_f32 + size_t(col0 + j) * ep.ld_f32_t + row;
+        if (ep.atomic_f32) red_add_f32(op, acc[j]); else *op = acc[j];
+      }
+    }
+  }
+  // ---- column sums over the 32 rows of this warp (bias gradient)
+  if (ep.colsum != nullptr) {
+    // butterfly: after the 5 rounds lane L holds sum over lanes of column L (31 shuffles per 32 columns)
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (j < CHUNK) ? acc[j] : 0.f;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float send = up ? v[i] : v[i + s];
+        const float keep = up ? v[i + s] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, v[0]);
+  }
+}
 
 // A_MN / B_MN: the operand is stored "MN-major" = [K rows, M|N contiguous] (e.g. the
 // activations [batch, features] when the reduction runs over the batch, or a weight
@@ -272,136 +412,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int v = 0; v < 4; ++v) mk[v] = mk_next[v];
       if (col0 + CHUNK < N) load_mask(mk_next, col0 + CHUNK);   // prefetch the next chunk's mask
       tmem_ld_wait();
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < CHUNK; ++j) {
-        float v = __uint_as_float(r[j]) * ep.alpha;
-        if (have_bias) v += s_bias[c0 + j];
-        if (ep.relu) v = fmaxf(v, 0.f);
-        acc[j] = v;
-      }
-      if (have_mask) {
-        if (row_ok && vec_ok) {
-          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(mk);
-#pragma unroll
-          for (int j = 0; j < CHUNK; ++j) acc[j] = (__bfloat162float(mb[j]) > 0.f) ? acc[j] : 0.f;
-        } else if (row_ok) {
-          for (int j = 0; j < CHUNK; ++j)
-            if (col0 + j < N) acc[j] = (__bfloat162float(mrow[col0 + j]) > 0.f) ? acc[j] : 0.f;
-        }
-      }
-      // ---- row-major fp32 of the plain result (logits for inference / validation)
-      if (ep.out_f32 != nullptr && row_ok && ep.loss_kind != 0) {
-        float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
-        for (int j = 0; j < CHUNK; ++j)
-          if (col0 + j < N) op[j] = acc[j];
-      }
-      // ---- fused loss (single n-tile, N <= CHUNK): the thread owns the whole output row.
-      //      acc[] becomes dLoss/dOutput so the stores / column sums below emit dZ and db.
-      if (ep.loss_kind == 1) {          // softmax cross entropy, mean over M rows
-        const int y = row_ok ? ep.ce_labels[row + lbl_off] : 0;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) if (j < N) mx = fmaxf(mx, acc[j]);
-        float sum = 0.f, zy = 0.f;
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          if (j == y) zy = acc[j];
-          acc[j] = (j < N) ? __expf(acc[j] - mx) : 0.f;
-          sum += acc[j];
-        }
-        float li = row_ok ? (mx + __logf(sum) - zy) : 0.f;
-        const float inv = 1.f / sum;
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) acc[j] = (row_ok && j < N) ? (acc[j] * inv - (j == y ? 1.f : 0.f)) * ep.loss_scale : 0.f;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-        if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
-      } else if (ep.loss_kind == 2) {   // mean squared error over M x N
-        float li = 0.f;
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          float dlt = 0.f;
-          if (row_ok && j < N) dlt = acc[j] - ep.mse_target[size_t(row + lbl_off) * ep.ld_target + j];
-          li += dlt * dlt;
-          acc[j] = 2.f * dlt * ep.loss_scale;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-        if (lane == 0) red_add_f32(ep.loss_slot, li * ep.loss_scale);
-      }
-      if (!row_ok) {
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) acc[j] = 0.f;
-      }
-      // ---- row-major bf16
-      if (ep.out_bf16 != nullptr && row_ok) {
-        __nv_bfloat16* op = ep.out_bf16 + size_t(row) * ep.ld_out + col0;
-        if (vec_ok || (col0 + CHUNK <= ep.ld_out && ep.loss_kind != 0)) {
-          // (fused loss: the padding columns up to the pitch are written as zeros)
-#pragma unroll
-          for (int v = 0; v < CHUNK / 8; ++v) {
-            uint4 w;
-            w.x = pack_bf16x2(acc[8 * v + 0], acc[8 * v + 1]);
-            w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
-            w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]);
-            w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
-            if (col0 + 8 * v < ep.ld_out) reinterpret_cast<uint4*>(op)[v] = w;
-          }
-        } else {
-          for (int j = 0; j < CHUNK; ++j)
-            if (col0 + j < N) op[j] = __float2bfloat16(acc[j]);
-        }
-      }
-      // ---- row-major fp32 (store or red.add for split-K)
-      if (ep.out_f32 != nullptr && row_ok && ep.loss_kind == 0) {
-        float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
-        if (ep.atomic_f32) {
-          for (int j = 0; j < CHUNK; ++j)
-            if (col0 + j < N) red_add_f32(op + j, acc[j]);
-        } else if (vec_ok && (ep.ld_f32 & 3) == 0) {
-#pragma unroll
-          for (int v = 0; v < CHUNK / 4; ++v)
-            reinterpret_cast<float4*>(op)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
-        } else {
-          for (int j = 0; j < CHUNK; ++j)
-            if (col0 + j < N) op[j] = acc[j];
-        }
-      }
-      // ---- transposed stores: lanes hold consecutive rows -> coalesced along m
-      if (ep.out_t_bf16 != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          if (col0 + j < N && row_ok) ep.out_t_bf16[size_t(col0 + j) * ep.ld_out_t + row] = __float2bfloat16(acc[j]);
-        }
-      }
-      if (ep.out_t_f32 != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          if (col0 + j < N && row_ok) {
-            float* op = ep.out_t_f32 + size_t(col0 + j) * ep.ld_f32_t + row;
-            if (ep.atomic_f32) red_add_f32(op, acc[j]); else *op = acc[j];
-          }
-        }
-      }
-      // ---- column sums over the 32 rows of this warp (bias gradient)
-      if (ep.colsum != nullptr) {
-        // butterfly: after the 5 rounds lane L holds sum over lanes of column L (31 shuffles per 32 columns)
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (j < CHUNK) ? acc[j] : 0.f;
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-          const bool up = (lane & s) != 0;
-#pragma unroll
-          for (int i = 0; i < s; ++i) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-          }
-        }
-        if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, v[0]);
-      }
+      epilogue_chunk<CHUNK>(ep, r, mk, have_mask, mrow, have_bias, s_bias, c0, row, row_ok, col0, N, lane, lbl_off);
     }
   }
 
@@ -413,6 +424,173 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
   if (prof && threadIdx.x == 32) prof[6] = clock64();
+}
+
+
+// ----------------------------------------------------------------------------- persistent variant
+// One CTA per SM loops over output tiles (m fastest, so concurrently running CTAs share the B tile in L2).
+// The accumulator is double buffered in TMEM (2 x BLOCK_N columns): while the epilogue warps drain tile t,
+// the MMA warp already accumulates tile t+1, and the TMA producer runs ahead across tile boundaries through
+// the same smem ring.  Used for large problems (tiles > #SMs): big-batch Linear layers and conv GEMMs.
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                            const GemmEpilogue ep, int M, int N, int K) {
+  using S = GemmSmem<BLOCK_N>;
+  static_assert(BLOCK_N >= 64 && 2 * BLOCK_N <= 512, "persistent tiles are 64..256 wide");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + S::STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);              // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                                // k-block counter across tiles (smem ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          const int k0 = i * BLOCK_K;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t as = t & 1;
+        mbar_wait(&tmem_empty_bar[as], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BLOCK_N;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
+          const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16(tacc, da + ka * k, db + kb * k, idesc, (i | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    constexpr int CHUNK = 32;
+    const bool have_bias = ep.bias != nullptr;
+    const bool have_mask = ep.mask_src != nullptr;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      const uint32_t as = t & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's s_bias readers are done
+      if (have_bias)
+        for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (n0 + c < N) ? ep.bias[n0 + c] : 0.f;
+      const __nv_bfloat16* mrow = have_mask ? ep.mask_src + size_t(row_ok ? row : 0) * ep.ld_mask : nullptr;
+      uint4 mk[4], mk_next[4];
+      auto load_mask = [&](uint4 (&dst)[4], int col0) {
+        if (have_mask && row_ok && col0 + CHUNK <= N) {
+          const uint4* mp = reinterpret_cast<const uint4*>(mrow + col0);
+#pragma unroll
+          for (int v = 0; v < CHUNK / 8; ++v) dst[v] = mp[v];
+        }
+      };
+      load_mask(mk_next, n0);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full_bar[as], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+        const int col0 = n0 + c0;
+        const bool live = col0 < N;                            // warp-uniform
+        uint32_t r[32];
+        if (live) {
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + uint32_t(c0), r);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) mk[v] = mk_next[v];
+          if (col0 + CHUNK < N) load_mask(mk_next, col0 + CHUNK);
+          tmem_ld_wait();
+        }
+        if (c0 + CHUNK >= BLOCK_N || col0 + CHUNK >= N) {
+          // last TMEM read of this tile is complete: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+        if (!live) break;
+        epilogue_chunk<CHUNK>(ep, r, mk, have_mask, mrow, have_bias, s_bias, c0, row, row_ok, col0, N, lane, 0);
+        if (col0 + CHUNK >= N) break;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
 }
 
 // ----------------------------------------------------------------------------- host
@@ -475,6 +653,36 @@ static cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const
   return launch_kernel(gemm_bf16_tn_kernel<BN, A_MN, B_MN>, grid, dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, ep, win, peer, M, N, K, kb_per);
 }
 
+template <int BN, bool A_MN, bool B_MN>
+static cudaError_t launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                                     cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool attr_set = false;
+  static int num_sms = 148;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  return launch_kernel(gemm_bf16_persistent_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, ep, M, N, K);
+}
+
+template <bool A_MN, bool B_MN>
+static cudaError_t dispatch_persistent(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
+                                       int N, int K, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_persistent<64, A_MN, B_MN>(ta, tb, ep, M, N, K, stream);
+    case 128: return launch_persistent<128, A_MN, B_MN>(ta, tb, ep, M, N, K, stream);
+    case 256: return launch_persistent<256, A_MN, B_MN>(ta, tb, ep, M, N, K, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <bool A_MN, bool B_MN>
 static cudaError_t dispatch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
                                const GemmWindow& win, const GemmPeerB& peer, int M, int N, int K, int split_k,
@@ -521,6 +729,17 @@ int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, 
   else rc = b_mn ? make_tmap_bf16_2d(&tb, B, b_krows, N, ldb, BLOCK_K) : make_tmap_bf16_2d(&tb, B, N, K, ldb, block_n);
   if (rc) return rc;
   cudaError_t e;
+  // Large problems: persistent CTAs with a double-buffered TMEM accumulator (epilogue overlaps the next tile's MMAs).
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+  const bool persistent = g_persistent_mode != 0 && block_n >= 64 && split_k == 1 && peer.world == 0 && win.flags == 0 &&
+                          ep->loss_kind == 0 && ep->prof == nullptr && (g_persistent_mode == 2 || tiles > 148);
+  if (persistent) {
+    if (a_mn && b_mn) e = dispatch_persistent<true, true>(block_n, ta, tb, *ep, M, N, K, stream);
+    else if (a_mn) e = dispatch_persistent<true, false>(block_n, ta, tb, *ep, M, N, K, stream);
+    else if (b_mn) e = dispatch_persistent<false, true>(block_n, ta, tb, *ep, M, N, K, stream);
+    else e = dispatch_persistent<false, false>(block_n, ta, tb, *ep, M, N, K, stream);
+    return e == cudaSuccess ? 0 : 1000 + int(e);
+  }
   if (a_mn && b_mn) e = dispatch_bn<true, true>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
   else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
   else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);

@@ -507,3 +507,29 @@ def test_gemm_k_ag_gathers_weights_from_sharded_fp32_arena(C):
     W2 = flat2[64:64 + O2 * I2].view(O2, I2).to(torch.bfloat16).float()
     ref2 = torch.nn.functional.cross_entropy(a.float() @ W2.t() + flat2[3008:3008 + O2], labels.long())
     torch.testing.assert_close(loss[0], ref2, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_gemm_persistent_variant(C, a_mn, b_mn, block_n):
+    """Persistent CTAs + double-buffered TMEM accumulator: many tiles per CTA, ragged edges, fused epilogue."""
+    M, N, K = 2000, 1100, 520
+    A = _mk(K, M, 0.5, 70) if a_mn else _mk(M, K, 0.5, 70)
+    B = _mk(K, N, 0.5, 71) if b_mn else _mk(N, K, 0.5, 71)
+    bias = torch.randn(N, device=dev())
+    mask = torch.relu(_mk(M, N, 1.0, 72))
+    ref = ((A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t()) + bias)
+    ref = torch.relu(ref) * (mask.float() > 0)
+    out = torch.zeros(M, _pad8(N), dtype=torch.bfloat16, device=dev())[:, :N]
+    o32 = torch.zeros(M, _pad8(N), dtype=torch.float32, device=dev())[:, :N]
+    cs = torch.zeros(N, device=dev())
+    C.set_persistent_mode(2)
+    try:
+        C.gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=bias, relu=True, mask_src=mask, out_bf16=out, out_f32=o32, colsum=cs,
+                    block_n=block_n)
+        torch.cuda.synchronize()
+    finally:
+        C.set_persistent_mode(1)
+    torch.testing.assert_close(o32, ref, rtol=2e-3, atol=0.15)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=0.2)
+    torch.testing.assert_close(cs, ref.sum(0), rtol=2e-2, atol=2.0)
