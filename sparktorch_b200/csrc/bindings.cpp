@@ -36,7 +36,8 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
                int64_t split_k, int64_t loss_kind, const OptT& labels, const OptT& target, const OptT& loss_slot,
                double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags,
                const OptT& prof, const std::vector<int64_t>& peer_ptrs, int64_t peer_shard_elems, int64_t peer_w_off,
-               int64_t peer_bias_off, bool peer_fill_local) {
+               int64_t peer_bias_off, bool peer_fill_local, const std::vector<int64_t>& push_deltas, int64_t push_me,
+               int64_t push_mask, const OptT& push_state) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
   c10::cuda::CUDAGuard guard(A.device());
@@ -67,6 +68,13 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
     win.window_rows = window_rows; win.n_windows = n_windows > 0 ? n_windows : 1; win.flags = int(win_flags);
     if (win_flags & 1) a_rows_total = A.size(0);
     if (win_flags & 2) b_rows_total = B.size(0);
+  }
+  if (!push_deltas.empty() && push_mask != 0) {
+    TORCH_CHECK(push_deltas.size() % 2 == 0 && push_deltas.size() <= 16 && push_state.has_value(), "push: [2][world] deltas + state");
+    ep.push_world = int(push_deltas.size() / 2); ep.push_me = int(push_me); ep.push_mask = int(push_mask);
+    for (int par = 0; par < 2; ++par)
+      for (int p = 0; p < ep.push_world; ++p) ep.push_delta[par][p] = push_deltas[par * ep.push_world + p];
+    ep.push_state = reinterpret_cast<const st::StepState*>(push_state->data_ptr());
   }
   st::GemmPeerB peer;
   if (!peer_ptrs.empty()) {
@@ -186,7 +194,8 @@ class Updater {
           std::vector<int64_t> wbf16_ptrs, std::vector<int64_t> flag_ptrs, int64_t mc_grad_ptr, const OptT& m, const OptT& v,
           const Tensor& state, const OptT& loss_hist, int64_t host_mailbox_ptr, const Tensor& segs, int64_t numel,
           int64_t tail, int64_t kind, double lr, double beta1, double beta2, double eps, double weight_decay, double momentum,
-          double dampening, bool nesterov, bool maximize, int64_t patience, bool zero_grads)
+          double dampening, bool nesterov, bool maximize, int64_t patience, bool zero_grads, int64_t recv_local_ptr,
+          int64_t recv_stride)
       : state_(state), segs_(segs), m_(m), v_(v), loss_hist_(loss_hist) {
     TORCH_CHECK(world >= 1 && world <= 8, "world size 1..8 (one NVSwitch domain)");
     a_ = st::UpdateArgs{};
@@ -212,8 +221,12 @@ class Updater {
     a_.kind = int(kind); a_.lr = float(lr); a_.beta1 = float(beta1); a_.beta2 = float(beta2); a_.eps = float(eps);
     a_.weight_decay = float(weight_decay); a_.momentum = float(momentum); a_.dampening = float(dampening);
     a_.nesterov = nesterov; a_.maximize = maximize; a_.patience = int(patience); a_.zero_grads = zero_grads;
+    a_.recv_local = reinterpret_cast<float*>(recv_local_ptr); a_.recv_stride = recv_stride;
   }
-  void step() { check(st::allreduce_update(a_, cur_stream()), "allreduce_update"); }
+  void step() {
+    if (a_.recv_local != nullptr) check(st::allreduce_push_update(a_, cur_stream()), "allreduce_push_update");
+    else check(st::allreduce_update(a_, cur_stream()), "allreduce_update");
+  }
   void publish() { check(st::publish_params(a_, cur_stream()), "publish_params"); }
   void set_lr(double lr) { a_.lr = float(lr); }
 
@@ -393,7 +406,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("loss_slot") = py::none(), py::arg("loss_scale") = 1.0, py::arg("win_state") = py::none(),
         py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0,
         py::arg("prof") = py::none(), py::arg("peer_ptrs") = std::vector<int64_t>{}, py::arg("peer_shard_elems") = 0,
-        py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false);
+        py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false,
+        py::arg("push_deltas") = std::vector<int64_t>{}, py::arg("push_me") = 0, py::arg("push_mask") = 0,
+        py::arg("push_state") = py::none());
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);
@@ -416,7 +431,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<Updater>(m, "Updater")
       .def(py::init<int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,
                     int64_t, const OptT&, const OptT&, const Tensor&, const OptT&, int64_t, const Tensor&, int64_t, int64_t,
-                    int64_t, double, double, double, double, double, double, double, bool, bool, int64_t, bool>())
+                    int64_t, double, double, double, double, double, double, double, bool, bool, int64_t, bool, int64_t, int64_t>())
       .def("step", &Updater::step)
       .def("publish", &Updater::publish)
       .def("set_lr", &Updater::set_lr);

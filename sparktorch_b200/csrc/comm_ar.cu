@@ -327,6 +327,161 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
   }
 }
 
+// ----------------------------------------------------------------------------- one-shot push variant
+// For small arenas the exchange is latency bound, so the data movement is taken off the critical path entirely:
+// the weight-gradient GEMMs (and the bias-gradient / loss reductions) mirror every write of the gradient arena into
+// "their" receive slot on every peer while they compute (GemmEpilogue::push_*).  When this kernel starts, all it
+// needs is ONE flag exchange ("my pushes are complete"); after that every operand of the reduction is LOCAL:
+//     g = (local + sum_p recv[parity][p]) / W  ->  Adam/SGD on the full replica (m, v replicated)  ->  fp32 + bf16
+// No second barrier: receive slots are double buffered by iteration parity - a peer can only write slot parity
+// (t+2)&1 after it has seen my flag of step t+1, which I raise after this kernel (incl. its clearing of the slots)
+// has finished.
+__global__ void __launch_bounds__(AR_THREADS) allreduce_push_update_kernel(const UpdateArgs a) {
+  __shared__ ParamSegment s_segs[MAX_SEGS_SMEM];
+  __shared__ uint32_t s_epoch;
+  __shared__ int s_stop, s_stop_now, s_last;
+  __shared__ float s_loss;
+  __shared__ OptConsts s_oc;
+  __shared__ long long s_step1;
+  const int W = a.world, me = a.rank;
+  const ParamSegment* segs = a.segs;
+  if (a.n_segs <= MAX_SEGS_SMEM) {
+    for (int i = threadIdx.x; i < a.n_segs; i += blockDim.x) s_segs[i] = a.segs[i];
+    segs = s_segs;
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    s_epoch = a.state->epoch + 1;
+    s_stop = 0; s_stop_now = 0; s_loss = 0.f;
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const int par = int(a.state->iter & 1);
+  // "my pushes are complete" (they were issued by earlier kernels of this stream; release is cumulative over them)
+  if (W > 1) block_barrier_all_gpus<true>(a.flags, W, me, 0, epoch);
+
+  const float* rbase = a.recv_local + int64_t(par) * W * a.recv_stride;
+  if (threadIdx.x == 0) {
+    float loss = 0.f, votes = 0.f;
+    for (int p = 0; p < W; ++p) {
+      const float* tp = (p == me) ? (a.grad[me] + a.numel) : (rbase + p * a.recv_stride + a.numel);
+      loss += tp[0];
+      votes += tp[1];
+    }
+    loss /= float(W);
+    int stop_now = 0;
+    const StepState st0 = *a.state;
+    if (st0.stopped) {
+      s_stop = 1;
+    } else if (a.patience > 0) {
+      if (!st0.es_seeded) {
+      } else if (isnan(loss)) {
+        stop_now = 1;
+      } else {
+        const uint32_t bad = (loss < st0.es_best) ? 0u : st0.es_bad + 1u;
+        if (bad >= uint32_t(a.patience)) stop_now = 1;
+      }
+      if (votes > 0.f) stop_now = 1;
+      s_stop = stop_now; s_stop_now = stop_now;
+    }
+    s_loss = loss;
+    const int64_t st1 = st0.step + 1;
+    s_step1 = st1;
+    OptConsts t{1.f, 1.f};
+    if (a.kind != 0) {
+      t.bc1_inv = 1.f / (1.f - powf(a.beta1, float(st1)));
+      t.bc2_inv_sqrt = rsqrtf(1.f - powf(a.beta2, float(st1)));
+    }
+    s_oc = t;
+  }
+  __syncthreads();
+  const bool skip_update = s_stop != 0;
+  const OptConsts oc = s_oc;
+  const bool first = s_step1 == 1;
+  const float inv_w = 1.f / float(W);
+  const int64_t n4 = a.numel >> 2;
+  const bool has_m = (a.kind != 0) || (a.momentum != 0.f);
+  float4* G = reinterpret_cast<float4*>(a.grad[me]);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i4 < n4; i4 += int64_t(gridDim.x) * blockDim.x) {
+    // canonical summation order (rank 0 .. W-1, the local arena standing in for slot `me`): every replica adds
+    // the same numbers in the same order, so all ranks compute bit-identical parameters
+    float4 g = z4;
+    for (int p = 0; p < W; ++p) {
+      float4* rp = (p == me) ? (G + i4) : (reinterpret_cast<float4*>(const_cast<float*>(rbase) + p * a.recv_stride) + i4);
+      const float4 q = *rp;
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+      *rp = z4;                                  // cleared for the next iteration of this parity
+    }
+    if (skip_update) continue;
+    g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
+    float4 p = reinterpret_cast<const float4*>(a.param[me])[i4];
+    float4 m = z4, v = z4;
+    if (has_m) m = reinterpret_cast<const float4*>(a.m)[i4];
+    if (a.kind != 0) v = reinterpret_cast<const float4*>(a.v)[i4];
+    p.x = opt_update_one(a, oc, p.x, g.x, m.x, v.x, first);
+    p.y = opt_update_one(a, oc, p.y, g.y, m.y, v.y, first);
+    p.z = opt_update_one(a, oc, p.z, g.z, m.z, v.z, first);
+    p.w = opt_update_one(a, oc, p.w, g.w, m.w, v.w, first);
+    if (has_m) reinterpret_cast<float4*>(a.m)[i4] = m;
+    if (a.kind != 0) reinterpret_cast<float4*>(a.v)[i4] = v;
+    reinterpret_cast<float4*>(a.param[me])[i4] = p;
+    const int64_t e = i4 << 2;
+    const ParamSegment sg = segs[find_segment(segs, a.n_segs, e)];
+    if (sg.w_off >= 0) {
+      const int64_t local = e - sg.offset, count = int64_t(sg.rows) * sg.cols;
+      __nv_bfloat16* wb = a.wbf16[me];
+      const float pv[4] = {p.x, p.y, p.z, p.w};
+      if ((sg.cols & 3) == 0 && (sg.w_ld & 3) == 0 && (sg.w_off & 3) == 0 && local + 3 < count) {
+        const int row = int(local / sg.cols), col = int(local % sg.cols);
+        uint2 h;
+        h.x = pack_bf16x2(pv[0], pv[1]);
+        h.y = pack_bf16x2(pv[2], pv[3]);
+        *reinterpret_cast<uint2*>(wb + sg.w_off + int64_t(row) * sg.w_ld + col) = h;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (local + j < count) wb[sg.w_off + int64_t((local + j) / sg.cols) * sg.w_ld + int((local + j) % sg.cols)] = __float2bfloat16(pv[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&a.state->blocks_done, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    StepState* st = a.state;
+    st->blocks_done = 0;
+    st->epoch = epoch;
+    for (int k = 0; k < a.tail; ++k) {
+      a.grad[me][a.numel + k] = 0.f;
+      for (int p = 0; p < W; ++p)
+        if (p != me) const_cast<float*>(rbase)[p * a.recv_stride + a.numel + k] = 0.f;
+    }
+    const int64_t it = st->iter;
+    if (!st->stopped) {
+      if (a.loss_hist != nullptr && it < a.max_iters) a.loss_hist[it] = s_loss;
+      st->last_loss = s_loss;
+      if (a.patience > 0) {
+        if (!st->es_seeded) { st->es_seeded = 1; st->es_best = s_loss; st->es_bad = 0; }
+        else if (!isnan(s_loss)) {
+          if (s_loss < st->es_best) { st->es_best = s_loss; st->es_bad = 0; } else { st->es_bad += 1; }
+        }
+      }
+      if (s_stop_now) st->stopped = 1; else st->step += 1;
+      st->iter = it + 1;
+      if (a.host_mailbox != nullptr) {
+        a.host_mailbox[2] = __float_as_uint(s_loss);
+        a.host_mailbox[1] = uint32_t(it + 1);
+        a.host_mailbox[0] = st->stopped;
+      }
+    }
+  }
+}
+
 static int ar_grid(int64_t numel, int world) {
   const int64_t n4 = (numel >> 2);
   const int64_t per = (n4 + world - 1) / world;
@@ -339,6 +494,11 @@ static int ar_grid(int64_t numel, int world) {
 int allreduce_update(const UpdateArgs& a, cudaStream_t stream) {
   if (a.world > 8 || (a.numel & 63)) return -1;
   return int(launch_kernel(allreduce_update_kernel<0>, dim3(ar_grid(a.numel, a.world)), dim3(AR_THREADS), 0, stream, a));
+}
+
+int allreduce_push_update(const UpdateArgs& a, cudaStream_t stream) {
+  if (a.world > 8 || (a.numel & 63) || a.recv_local == nullptr) return -1;
+  return int(launch_kernel(allreduce_push_update_kernel, dim3(ar_grid(a.numel, 1)), dim3(AR_THREADS), 0, stream, a));
 }
 
 int publish_params(const UpdateArgs& a, cudaStream_t stream) {

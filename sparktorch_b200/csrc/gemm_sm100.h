@@ -7,6 +7,8 @@
 
 namespace st {
 
+struct StepState;                         // kernels.h
+
 struct GemmEpilogue {
   float alpha = 1.f;
   const float* bias = nullptr;            // [N] added per column
@@ -31,6 +33,14 @@ struct GemmEpilogue {
   int64_t ld_target = 0;
   float* loss_slot = nullptr;             // += loss * loss_scale
   float loss_scale = 1.f;                 // 1/M (CE) or 1/(M*N) (MSE)
+  // ---- GEMM -> all-gather push (one-shot gradient exchange): every write into the local gradient arena is
+  // mirrored into the receive slot this rank owns on every peer GPU (peer-mapped NVLink stores / red.add issued
+  // from the epilogue, tile by tile, while other tiles are still being computed).  peer address = local + delta.
+  int push_world = 0;                     // 0: disabled
+  int push_me = 0;
+  int push_mask = 0;                      // 1: fp32 outputs, 2: colsum, 4: loss slot
+  long long push_delta[2][8] = {{0}};     // [parity of the iteration][peer] byte distance local arena -> my slot on that peer
+  const StepState* push_state = nullptr;  // parity = iter & 1
   // optional phase timestamps (SM clock64): [cta][8] = start, prologue done, dependencies met,
   // first operand tile landed, accumulator complete, epilogue done
   long long* prof = nullptr;
@@ -51,8 +61,6 @@ struct GemmPeerB {
   __nv_bfloat16* wb_local = nullptr;      // [N, ld_wb] local bf16 copy to fill (or null)
   int64_t ld_wb = 0;
 };
-
-struct StepState;                         // kernels.h
 
 // Mini-batch window taken on the device from StepState::iter (no gather kernel, no host in the loop).
 struct GemmWindow {

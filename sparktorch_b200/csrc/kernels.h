@@ -87,10 +87,14 @@ struct UpdateArgs {
   int nesterov, maximize;
   int patience;               // <=0: no early stopping
   int zero_grads;             // zero the local gradient arena after the exchange
+  // one-shot "push" exchange (small arenas): peers have already written their gradients into my receive slots
+  float* recv_local;          // [2 parities][world][recv_stride] on THIS gpu (slot [par][me] unused)
+  int64_t recv_stride;        // floats per slot (>= numel + tail)
 };
 constexpr int AR_MAX_BLOCKS = 256;
 constexpr int AR_FLAG_WORDS = 2 * 8 * AR_MAX_BLOCKS;
 int allreduce_update(const UpdateArgs& a, cudaStream_t stream);
+int allreduce_push_update(const UpdateArgs& a, cudaStream_t stream);   // one-shot: gradients were pushed by the GEMM epilogues
 int publish_params(const UpdateArgs& a, cudaStream_t stream);   // (re)build bf16 copies from fp32 master, no exchange
 int allreduce_sum_f32(float* const* bufs, uint32_t* const* flags, StepState* state, int world, int rank, int64_t n,
                       int use_twoshot, cudaStream_t stream);

@@ -89,12 +89,18 @@ class FusedUpdate:
     """Owns the symmetric arenas + the native ``Updater`` for one model replica."""
 
     def __init__(self, numel: int, spec: OptSpec, world: int, rank: int, device: torch.device, patience: int,
-                 max_iters: int, wbf16_elems: int = 0, use_multicast: bool = True):
+                 max_iters: int, wbf16_elems: int = 0, use_multicast: bool = True, exchange: str = "twoshot"):
         C = native.load(required=True)
         self.C = C
         self.numel, self.world, self.rank, self.device = numel, world, rank, device
+        # 'push': one-shot exchange - the GEMM epilogues mirror gradient writes into receive slots on every peer
+        # (double buffered by iteration parity); optimizer state is replicated.  'twoshot': reduce-scatter/publish.
+        self.exchange = exchange if world > 1 else "twoshot"
+        self.recv_stride = _round_up(numel + TAIL, 64)
         self.block = SymmBlock(device, world, rank)
         self.block.reserve("grad", (numel + TAIL + 60) * 4)
+        if self.exchange == "push":
+            self.block.reserve("recv", 2 * world * self.recv_stride * 4)
         self.block.reserve("param", numel * 4)
         if wbf16_elems:
             self.block.reserve("wbf16", wbf16_elems * 2)
@@ -103,7 +109,7 @@ class FusedUpdate:
         self.grad = self.block.view("grad", torch.float32, numel + TAIL)
         self.param = self.block.view("param", torch.float32, numel)
         self.wbf16 = self.block.view("wbf16", torch.bfloat16, wbf16_elems) if wbf16_elems else None
-        n_state = opt_state_elems(numel, world)
+        n_state = numel if self.exchange == "push" else opt_state_elems(numel, world)
         self.m = torch.zeros(n_state, device=device) if spec.n_state >= 1 else None
         self.v = torch.zeros(n_state, device=device) if spec.n_state >= 2 else None
         self.state = torch.zeros(C.step_state_bytes() // 4, dtype=torch.int32, device=device)
@@ -126,7 +132,18 @@ class FusedUpdate:
             self.world, self.rank, self.block.peer_ptrs("grad"), self.block.peer_ptrs("param"),
             self.block.peer_ptrs("wbf16") if self.wbf16 is not None else [], flags, mc, self.m, self.v, self.state,
             self.loss_hist, self.mailbox.data_ptr(), self._segs, self.numel, TAIL, s.kind_id, s.lr, s.beta1, s.beta2,
-            s.eps, s.weight_decay, s.momentum, s.dampening, s.nesterov, s.maximize, self.patience, zero_grads)
+            s.eps, s.weight_decay, s.momentum, s.dampening, s.nesterov, s.maximize, self.patience, zero_grads,
+            self.block.peer_ptrs("recv")[self.rank] if self.exchange == "push" else 0, self.recv_stride)
+
+    def push_kw(self, mask: int) -> dict:
+        """Arguments that make a GEMM mirror its gradient-arena writes into my slot on every peer."""
+        if self.exchange != "push" or mask == 0:
+            return {}
+        W, me, st = self.world, self.rank, self.recv_stride
+        local = self.block.peer_ptrs("grad")[me]
+        peers = self.block.peer_ptrs("recv")
+        deltas = [peers[p] + ((par * W + me) * st) * 4 - local for par in range(2) for p in range(W)]
+        return dict(push_deltas=deltas, push_me=me, push_mask=mask, push_state=self.state)
 
     # StepState accessors (int32 view: epoch, blocks_done, step(lo,hi), iter(lo,hi), stopped, ...)
     def iters_done(self) -> int:

@@ -170,10 +170,15 @@ class FusedMLP:
         for l in range(1, L + 1):
             w_off.append(off)
             off += _pad(d[l] * _pad(d[l - 1]), 64)
+        fuse_loss = d[L] <= 32 and os.environ.get("SPARKTORCH_FUSE_LOSS", "1") == "1"
         if backend_factory is not None:      # hogwild: owner-sharded parameters, K-AG forward, remote-apply push
             self.fu = backend_factory(numel, off)
         else:
-            self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
+            # small arenas: one-shot exchange, gradients pushed to the peers by the GEMM epilogues themselves
+            want = os.environ.get("SPARKTORCH_EXCHANGE", "auto")
+            push = world > 1 and fuse_loss and (want == "push" or (want == "auto" and numel * 4 <= (8 << 20)))
+            self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off,
+                                  exchange="push" if push else "twoshot")
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
         pos = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
         rows, self.Wb, self.bias, self.gW, self.gb = [], [], [], [], []
@@ -210,7 +215,7 @@ class FusedMLP:
         self.train = self._alloc_acts(batch, backward=True)
         self.val = self._alloc_acts(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
-        self.fuse_loss = d[L] <= 32 and os.environ.get("SPARKTORCH_FUSE_LOSS", "1") == "1"
+        self.fuse_loss = fuse_loss
         self.window = None            # (n_windows, window_rows): batch = window of the resident partition
         self.side = torch.cuda.Stream(device=device) if os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None
 
@@ -233,6 +238,10 @@ class FusedMLP:
     def _gemm(self, A, a_mn, Bm, b_mn, M, N, K, **kw):
         self.C.gemm_bf16(A, a_mn, Bm, b_mn, M, N, K, **kw)
         self.n_launch += 1
+
+    def _push(self, mask: int) -> dict:
+        f = getattr(self.fu, "push_kw", None)
+        return f(mask) if f is not None else {}
 
     def _win(self, flags: int) -> dict:
         if self.window is None or flags == 0:
@@ -261,6 +270,7 @@ class FusedMLP:
                 kw["labels" if self.kind == "ce" else "target"] = buf["tgt"]
                 if train:
                     kw.update(out_bf16=buf["dz"][L], colsum=self.gb[L - 1])
+                kw.update(self._push(4 | (2 if train else 0)))      # loss (+ last bias gradient) go to the peers too
             else:
                 kw["out_f32"] = buf["logits"]
             kw.update(self._win(flags))
@@ -296,6 +306,7 @@ class FusedMLP:
             sk = self._split_k(d[l], d[l - 1], rows)
             wkw = dict(out_f32=self.gW[l - 1], atomic_f32=sk > 1, split_k=sk)
             wkw.update(self._win(2 if (windowed and l == 1) else 0))
+            wkw.update(self._push(1))                                  # GEMM -> all-gather: dW tiles land on every peer
             if side is not None and l > 1:
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -308,7 +319,8 @@ class FusedMLP:
                 # dgrad: dZ_{l-1} = (dZ_l W_l) * (A_{l-1} > 0); db_{l-1} = column sums
                 relu_prev = self.lowered.layers[l - 2].relu
                 self._gemm(dz[l], False, self.Wb[l - 1], True, rows, d[l - 1], d[l],
-                           mask_src=acts[l - 1] if relu_prev else None, out_bf16=dz[l - 1], colsum=self.gb[l - 2])
+                           mask_src=acts[l - 1] if relu_prev else None, out_bf16=dz[l - 1], colsum=self.gb[l - 2],
+                           **self._push(2))
         if side is not None:
             ev = torch.cuda.Event()
             ev.record(side)
@@ -541,7 +553,9 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     stopped = plan.fu.stopped()
     losses = plan.fu.loss_hist[:n_done].cpu().tolist()
     history = {
-        "engine": "fused_cnn" if is_cnn else "fused_mlp", "comm": "P2PFused" + ("+NVLS" if plan.fu.use_multicast else ""), "precision": "bf16",
+        "engine": "fused_cnn" if is_cnn else "fused_mlp",
+        "comm": ("P2PPush" if getattr(plan.fu, "exchange", "") == "push" else "P2PFused" + ("+NVLS" if plan.fu.use_multicast else "")),
+        "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
         "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
         "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes(),
