@@ -29,37 +29,48 @@ constexpr int CV_THREADS = 256;
 // x is addressed with explicit element strides (sb, sh, sw, sc), so NHWC activations, NCHW-flat
 // Spark rows and pooled (c,h,w)-ordered maps are all valid sources.  With a StepState the sample
 // index is offset by the device-side mini-batch window (see GemmWindow).
+// Thread <-> column k (so its (c, i, j) decomposition is computed once and global writes of a warp are
+// contiguous along k); a block walks IM2COL_ROWS output pixels.  Source reads of neighbouring pixels overlap
+// heavily and are served by L1.
+constexpr int IM2COL_ROWS = 64;
 __global__ void __launch_bounds__(CV_THREADS) im2col_nhwc_kernel(const Im2colArgs a) {
   pdl_wait();
   pdl_launch_dependents();
   const int64_t b_off = a.state != nullptr ? (a.state->iter % a.n_windows) * a.window_rows : 0;
   const int64_t M = int64_t(a.B) * a.OH * a.OW;
   const int kk = a.kh * a.kw;
-  const int64_t total = M * a.ld_col;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t m = e / a.ld_col;
-    const int k = int(e - m * a.ld_col);
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (k < a.K) {
-      const int c = k / kk, r = k - c * kk;
-      const int i = r / a.kw, j = r - i * a.kw;
-      const int ow = int(m % a.OW);
-      const int64_t t = m / a.OW;
-      const int oh = int(t % a.OH);
-      const int64_t b = t / a.OH;
-      const int h = oh * a.stride - a.pad + i, w = ow * a.stride - a.pad + j;
-      if (h >= 0 && h < a.H && w >= 0 && w < a.W) v = a.x[(b + b_off) * a.sb + int64_t(h) * a.sh + int64_t(w) * a.sw + int64_t(c) * a.sc];
+  const int64_t m_begin = int64_t(blockIdx.x) * IM2COL_ROWS;
+  const int64_t m_end = m_begin + IM2COL_ROWS < M ? m_begin + IM2COL_ROWS : M;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  // 2-D thread layout: tk threads along k (power of two covering the row pitch, <= 256), the rest along rows
+  int tk = 1;
+  while (tk < a.ld_col && tk < CV_THREADS) tk <<= 1;
+  const int tr = CV_THREADS / tk;
+  const int tx = threadIdx.x % tk, ty = threadIdx.x / tk;
+  for (int k = tx; k < a.ld_col; k += tk) {
+    const bool live = k < a.K;
+    const int c = live ? k / kk : 0, r = live ? k - c * kk : 0;
+    const int i = r / a.kw, j = r - i * a.kw;
+    const int64_t coff = int64_t(c) * a.sc;
+    for (int64_t m = m_begin + ty; m < m_end; m += tr) {
+      __nv_bfloat16 v = zero;
+      if (live) {
+        const int ow = int(m % a.OW);
+        const int64_t t = m / a.OW;
+        const int oh = int(t % a.OH);
+        const int64_t b = t / a.OH;
+        const int h = oh * a.stride - a.pad + i, w = ow * a.stride - a.pad + j;
+        if (h >= 0 && h < a.H && w >= 0 && w < a.W) v = a.x[(b + b_off) * a.sb + int64_t(h) * a.sh + int64_t(w) * a.sw + coff];
+      }
+      a.col[m * a.ld_col + k] = v;
     }
-    a.col[e] = v;
   }
 }
 
 int im2col_nhwc(const Im2colArgs& a, cudaStream_t stream) {
-  const int64_t total = int64_t(a.B) * a.OH * a.OW * a.ld_col;
-  int64_t g = (total + CV_THREADS * 4 - 1) / (CV_THREADS * 4);
-  if (g < 1) g = 1;
-  if (g > 148 * 16) g = 148 * 16;
-  return int(launch_kernel(im2col_nhwc_kernel, dim3(unsigned(g)), dim3(CV_THREADS), 0, stream, a));
+  const int64_t M = int64_t(a.B) * a.OH * a.OW;
+  const int64_t g = (M + IM2COL_ROWS - 1) / IM2COL_ROWS;
+  return int(launch_kernel(im2col_nhwc_kernel, dim3(unsigned(g < 1 ? 1 : g)), dim3(CV_THREADS), 0, stream, a));
 }
 
 // w: [Cout, ld_w] bf16 holding [Cout, Cin, kh, kw]; out: [Cin, ld_o] holding [Cin, Cout, kh, kw] with flipped taps
