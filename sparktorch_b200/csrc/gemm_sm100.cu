@@ -342,7 +342,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // the bias slice goes to shared memory, the first ReLU-mask chunk to registers.
     const int et = threadIdx.x - 64;           // 0..127
     const bool peer_b = !B_MN && peer.world > 0;
-    const bool have_bias = ep.bias != nullptr || (peer_b && peer.bias_off >= 0);
+    // with split-K every split adds into the same output: only split 0 contributes the bias
+    const bool have_bias = (ep.bias != nullptr || (peer_b && peer.bias_off >= 0)) && blockIdx.z == 0;
     if (peer_b && peer.bias_off >= 0) {
       for (int c = et; c < BLOCK_N; c += 128) {
         const int64_t f = peer.bias_off + n0 + c;

@@ -304,7 +304,8 @@ class FusedCNN:
                                     if (g["pool"] and not last) else None)
         # linear head
         buf["lin"] = [None] + [torch.zeros(rows, _pad(self.dl[l]), dtype=bf, device=dev)[:, : self.dl[l]] for l in range(1, self.L)]
-        buf["logits"] = torch.zeros(rows, _pad(self.dl[-1], 16), dtype=torch.float32, device=dev)[:, : self.dl[-1]]
+        buf["logits_full"] = torch.zeros(rows, _pad(self.dl[-1], 16), dtype=torch.float32, device=dev)
+        buf["logits"] = buf["logits_full"][:, : self.dl[-1]]
         if backward:
             buf["dz"] = [torch.zeros(rows, _pad(self.dl[l]), dtype=bf, device=dev)[:, : self.dl[l]] for l in range(0, self.L + 1)]
         buf["tgt"] = (torch.zeros(rows, dtype=torch.int32, device=dev) if self.kind == "ce"
@@ -368,7 +369,7 @@ class FusedCNN:
                 kw.update(self.peer_kw[id(m)])
             if not last:
                 kw["out_bf16"] = buf["lin"][l]
-            elif slot is not None and self.fuse_loss:
+            elif slot is not None and self.fuse_loss and not self._deep_head(rows):
                 kw.update(loss_kind=1 if self.kind == "ce" else 2, loss_slot=slot,
                           loss_scale=(1.0 / rows) if self.kind == "ce" else 1.0 / (rows * self.dl[-1]))
                 kw["labels" if self.kind == "ce" else "target"] = buf["tgt"]
@@ -377,14 +378,24 @@ class FusedCNN:
                 kw.update(self._win(4 if windowed else 0))
             else:
                 kw["out_f32"] = buf["logits"]
+                if last and slot is not None and self._deep_head(rows):
+                    # a [rows<=256, K>=2048] x [K, <=32] head is ONE tile: split K over many SMs (fp32 red.add into
+                    # the zeroed logits) and run the loss as its own small kernel instead of serialising on one SM
+                    buf["logits_full"].zero_()
+                    self.n_launch += 1
+                    kb = (self.dl[l - 1] + 63) // 64
+                    kw.update(atomic_f32=True, split_k=max(2, min(32, kb // 4)))
             self._gemm(a, False, self.Wb[id(m)], False, rows, self.dl[l], self.dl[l - 1], **kw)
             a = buf["lin"][l] if not last else None
-        if slot is not None and not self.fuse_loss:
+        if slot is not None and (not self.fuse_loss or self._deep_head(rows)):
             dz = buf["dz"][self.L] if train else None
             db = self.gb[id(low.linears[-1].module)] if train else None
             fn = self.C.softmax_ce if self.kind == "ce" else self.C.mse_loss
             fn(buf["logits"], buf["tgt"], self.dl[-1], slot, dz, None, db, _pad(self.dl[-1]))
             self.n_launch += 1
+
+    def _deep_head(self, rows: int) -> bool:
+        return rows <= 256 and self.dl[-2] >= 2048 and os.environ.get("SPARKTORCH_SPLIT_HEAD", "1") == "1"
 
     def _split_k(self, M: int, N: int, K: int) -> int:
         tiles = ((M + 127) // 128) * ((N + 63) // 64)
