@@ -421,7 +421,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   // 128B swizzle: 16-byte chunk index XOR (row mod 8)
                   *reinterpret_cast<uint4*>(sb + n * 128 + ((c ^ (n & 7)) << 4)) = w;
                   const int gn = n0 + n, gk = k0 + c * 8;
-                  if (peer.wb_local != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && gn < N && gk < peer.ld_wb)
+                  if (peer.wb_local != nullptr && blockIdx.y == 0 && gn < N && gk < peer.ld_wb)
                     *reinterpret_cast<uint4*>(peer.wb_local + int64_t(gn) * peer.ld_wb + gk) = w;
                 }
               }
