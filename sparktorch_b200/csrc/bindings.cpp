@@ -46,8 +46,16 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
   ep.relu = relu ? 1 : 0;
   ep.atomic_f32 = atomic_f32 ? 1 : 0;
   if (bias) { TORCH_CHECK(bias->scalar_type() == at::kFloat && bias->numel() >= N); ep.bias = bias->data_ptr<float>(); }
-  if (mask_src) { req_2d(*mask_src, at::kBFloat16, "mask_src"); ep.mask_src = bf16p(*mask_src); ep.ld_mask = mask_src->stride(0); }
-  if (out_bf16) { req_2d(*out_bf16, at::kBFloat16, "out_bf16"); ep.out_bf16 = bf16pm(*out_bf16); ep.ld_out = out_bf16->stride(0); }
+  if (mask_src) {
+    req_2d(*mask_src, at::kBFloat16, "mask_src");
+    TORCH_CHECK(mask_src->stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(mask_src->data_ptr()) & 15) == 0, "mask_src: pitch must be a multiple of 8 elements, base 16-byte aligned");
+    ep.mask_src = bf16p(*mask_src); ep.ld_mask = mask_src->stride(0);
+  }
+  if (out_bf16) {
+    req_2d(*out_bf16, at::kBFloat16, "out_bf16");
+    TORCH_CHECK(out_bf16->stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16->data_ptr()) & 15) == 0, "out_bf16: pitch must be a multiple of 8 elements, base 16-byte aligned");
+    ep.out_bf16 = bf16pm(*out_bf16); ep.ld_out = out_bf16->stride(0);
+  }
   if (out_t_bf16) { req_2d(*out_t_bf16, at::kBFloat16, "out_t_bf16"); ep.out_t_bf16 = bf16pm(*out_t_bf16); ep.ld_out_t = out_t_bf16->stride(0); }
   if (out_f32) { req_2d(*out_f32, at::kFloat, "out_f32"); ep.out_f32 = out_f32->data_ptr<float>(); ep.ld_f32 = out_f32->stride(0); }
   if (out_t_f32) { req_2d(*out_t_f32, at::kFloat, "out_t_f32"); ep.out_t_f32 = out_t_f32->data_ptr<float>(); ep.ld_f32_t = out_t_f32->stride(0); }

@@ -517,7 +517,8 @@ def test_gemm_persistent_variant(C, a_mn, b_mn, block_n):
     A = _mk(K, M, 0.5, 70) if a_mn else _mk(M, K, 0.5, 70)
     B = _mk(K, N, 0.5, 71) if b_mn else _mk(N, K, 0.5, 71)
     bias = torch.randn(N, device=dev())
-    mask = torch.relu(_mk(M, N, 1.0, 72))
+    mask = _mk(M, N, 1.0, 72)
+    mask.clamp_(min=0)                       # keep the padded pitch (torch.relu would return a dense copy)
     ref = ((A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t()) + bias)
     ref = torch.relu(ref) * (mask.float() > 0)
     out = torch.zeros(M, _pad8(N), dtype=torch.bfloat16, device=dev())[:, :N]
