@@ -35,8 +35,8 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
                const OptT& out_f32, const OptT& out_t_f32, bool atomic_f32, const OptT& colsum, int64_t block_n,
                int64_t split_k, int64_t loss_kind, const OptT& labels, const OptT& target, const OptT& loss_slot,
                double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags,
-               const OptT& prof, const std::vector<int64_t>& peer_ptrs, int64_t peer_shard_elems, int64_t peer_w_off,
-               int64_t peer_bias_off, bool peer_fill_local, const std::vector<int64_t>& push_deltas, int64_t push_me,
+               const OptT& prof, const OptT& peer_table, int64_t peer_shard_elems, int64_t peer_w_off,
+               int64_t peer_bias_off, bool peer_fill_local, const OptT& push_table, int64_t push_me,
                int64_t push_mask, const OptT& push_state) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
@@ -77,18 +77,19 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
     if (win_flags & 1) a_rows_total = A.size(0);
     if (win_flags & 2) b_rows_total = B.size(0);
   }
-  if (!push_deltas.empty() && push_mask != 0) {
-    TORCH_CHECK(push_deltas.size() % 2 == 0 && push_deltas.size() <= 16 && push_state.has_value(), "push: [2][world] deltas + state");
-    ep.push_world = int(push_deltas.size() / 2); ep.push_me = int(push_me); ep.push_mask = int(push_mask);
-    for (int par = 0; par < 2; ++par)
-      for (int p = 0; p < ep.push_world; ++p) ep.push_delta[par][p] = push_deltas[par * ep.push_world + p];
+  if (push_table && push_mask != 0) {
+    TORCH_CHECK(push_table->is_cuda() && push_table->scalar_type() == at::kLong && push_table->numel() % 2 == 0 &&
+                push_table->numel() <= 16 && push_state.has_value(), "push: device int64 table [2][world] + state");
+    ep.push_world = int(push_table->numel() / 2); ep.push_me = int(push_me); ep.push_mask = int(push_mask);
+    ep.push_delta = reinterpret_cast<const long long*>(push_table->data_ptr());
     ep.push_state = reinterpret_cast<const st::StepState*>(push_state->data_ptr());
   }
   st::GemmPeerB peer;
-  if (!peer_ptrs.empty()) {
-    TORCH_CHECK(peer_ptrs.size() <= 8 && peer_shard_elems > 0, "K-AG: up to 8 owners");
-    peer.world = int(peer_ptrs.size());
-    for (size_t r = 0; r < peer_ptrs.size(); ++r) peer.param[r] = reinterpret_cast<const float*>(peer_ptrs[r]);
+  if (peer_table) {
+    TORCH_CHECK(peer_table->is_cuda() && peer_table->scalar_type() == at::kLong && peer_table->numel() <= 8 && peer_shard_elems > 0,
+                "K-AG: device int64 table of up to 8 owner pointers");
+    peer.world = int(peer_table->numel());
+    peer.param = reinterpret_cast<const float* const*>(peer_table->data_ptr());
     peer.shard_elems = peer_shard_elems; peer.w_off = peer_w_off; peer.bias_off = peer_bias_off;
     if (peer_fill_local) { peer.wb_local = bf16pm(B); peer.ld_wb = B.stride(0); }
   }
@@ -413,9 +414,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("loss_kind") = 0, py::arg("labels") = py::none(), py::arg("target") = py::none(),
         py::arg("loss_slot") = py::none(), py::arg("loss_scale") = 1.0, py::arg("win_state") = py::none(),
         py::arg("window_rows") = 0, py::arg("n_windows") = 1, py::arg("win_flags") = 0,
-        py::arg("prof") = py::none(), py::arg("peer_ptrs") = std::vector<int64_t>{}, py::arg("peer_shard_elems") = 0,
+        py::arg("prof") = py::none(), py::arg("peer_table") = py::none(), py::arg("peer_shard_elems") = 0,
         py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false,
-        py::arg("push_deltas") = std::vector<int64_t>{}, py::arg("push_me") = 0, py::arg("push_mask") = 0,
+        py::arg("push_table") = py::none(), py::arg("push_me") = 0, py::arg("push_mask") = 0,
         py::arg("push_state") = py::none());
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);

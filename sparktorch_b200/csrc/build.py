@@ -48,6 +48,9 @@ def _run(cmd: List[str], verbose: bool) -> None:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("build step failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if cmd[0] == NVCC and "-o" in cmd:       # keep ptxas' resource report next to the object (registers, spills, stack)
+        with open(cmd[cmd.index("-o") + 1] + ".ptxas.txt", "w") as fh:
+            fh.write(r.stdout + r.stderr)
     if verbose and (r.stdout.strip() or r.stderr.strip()):
         print(r.stdout + r.stderr)
 
@@ -66,7 +69,7 @@ def build_all(verbose: bool = False, force: bool = False) -> str:
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
         return out
     nvcc_flags = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
-                         "-Xptxas", "-v" if verbose else "-O3"]
+                         "-Xptxas", "-v"]
     objs = []
     jobs = []
     for s in cu:

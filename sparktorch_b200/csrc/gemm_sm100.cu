@@ -46,14 +46,14 @@ struct GemmSmem {
 ST_DEVINL void push_store_f32(const GemmEpilogue& ep, int par, float* local, float v, bool atomic) {
   for (int p = 0; p < ep.push_world; ++p) {
     if (p == ep.push_me) continue;
-    float* q = reinterpret_cast<float*>(reinterpret_cast<char*>(local) + ep.push_delta[par][p]);
+    float* q = reinterpret_cast<float*>(reinterpret_cast<char*>(local) + ep.push_delta[par * ep.push_world + p]);
     if (atomic) red_add_f32(q, v); else *q = v;
   }
 }
 ST_DEVINL void push_store_f4(const GemmEpilogue& ep, int par, float4* local, const float4& v) {
   for (int p = 0; p < ep.push_world; ++p) {
     if (p == ep.push_me) continue;
-    *reinterpret_cast<float4*>(reinterpret_cast<char*>(local) + ep.push_delta[par][p]) = v;
+    *reinterpret_cast<float4*>(reinterpret_cast<char*>(local) + ep.push_delta[par * ep.push_world + p]) = v;
   }
 }
 
@@ -76,10 +76,17 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
   }
   if (have_mask) {
     if (row_ok && vec_ok) {
-      const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(mk);
+      // decode the prefetched mask registers with constant indices only (no address-of: keeps them in registers)
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) acc[j] = (__bfloat162float(mb[j]) > 0.f) ? acc[j] : 0.f;
+      for (int j = 0; j < CHUNK; ++j) {
+        const uint4& q4 = mk[j >> 3];
+        const int wi = (j & 7) >> 1;
+        const uint32_t w = wi == 0 ? q4.x : (wi == 1 ? q4.y : (wi == 2 ? q4.z : q4.w));
+        const float mv = __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+        acc[j] = (mv > 0.f) ? acc[j] : 0.f;
+      }
     } else if (row_ok) {
+#pragma unroll
       for (int j = 0; j < CHUNK; ++j)
         if (col0 + j < N) acc[j] = (__bfloat162float(mrow[col0 + j]) > 0.f) ? acc[j] : 0.f;
     }
@@ -87,6 +94,7 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
   // ---- row-major fp32 of the plain result (logits for inference / validation)
   if (ep.out_f32 != nullptr && row_ok && ep.loss_kind != 0) {
     float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
+#pragma unroll
     for (int j = 0; j < CHUNK; ++j)
       if (col0 + j < N) op[j] = acc[j];
   }
@@ -149,6 +157,7 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
         if (col0 + 8 * v < ep.ld_out) reinterpret_cast<uint4*>(op)[v] = w;
       }
     } else {
+#pragma unroll
       for (int j = 0; j < CHUNK; ++j)
         if (col0 + j < N) op[j] = __float2bfloat16(acc[j]);
     }
@@ -157,6 +166,7 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
   if (ep.out_f32 != nullptr && row_ok && ep.loss_kind == 0) {
     float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col0;
     if (ep.atomic_f32) {
+#pragma unroll
       for (int j = 0; j < CHUNK; ++j)
         if (col0 + j < N) {
           red_add_f32(op + j, acc[j]);
@@ -170,6 +180,7 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
         if (push_f32) push_store_f4(ep, par, reinterpret_cast<float4*>(op) + v, w);
       }
     } else {
+#pragma unroll
       for (int j = 0; j < CHUNK; ++j)
         if (col0 + j < N) {
           op[j] = acc[j];

@@ -39,7 +39,9 @@ struct GemmEpilogue {
   int push_world = 0;                     // 0: disabled
   int push_me = 0;
   int push_mask = 0;                      // 1: fp32 outputs, 2: colsum, 4: loss slot
-  long long push_delta[2][8] = {{0}};     // [parity of the iteration][peer] byte distance local arena -> my slot on that peer
+  const long long* push_delta = nullptr;  // DEVICE table [2 parities][push_world]: byte distance local arena -> my slot on that peer
+                                          // (a table in global memory: dynamic indexing of kernel parameters would force the whole
+                                          //  parameter struct into local memory)
   const StepState* push_state = nullptr;  // parity = iter & 1
   // optional phase timestamps (SM clock64): [cta][8] = start, prologue done, dependencies met,
   // first operand tile landed, accumulator complete, epilogue done
@@ -54,7 +56,7 @@ struct GemmEpilogue {
 // written to a local bf16 copy (wb_local) for later consumers (dgrad).
 struct GemmPeerB {
   int world = 0;                          // 0: disabled
-  const float* param[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const float* const* param = nullptr;    // DEVICE table [world] of the owners' arena base pointers
   int64_t shard_elems = 0;
   int64_t w_off = 0;                      // flat offset of W[0,0]; row pitch = K
   int64_t bias_off = -1;                  // flat offset of the bias vector (or -1)

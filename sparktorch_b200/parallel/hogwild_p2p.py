@@ -168,6 +168,7 @@ class HogwildBackend:
         n4 = numel // 4
         self.shard_elems = ((n4 + world - 1) // world) * 4
         self.peer_param_ptrs = blk.peer_ptrs("param")
+        self.peer_table = torch.tensor(self.peer_param_ptrs, dtype=torch.int64, device=device)   # read by the K-AG GEMMs
         self.stripes = pick_stripes(numel, world, C.hw_max_stripes())
         self.updater = C.HogwildWorker(
             world, rank, self.stripes, blk.peer_ptrs("param"), blk.peer_ptrs("m") if spec.n_state >= 1 else [],

@@ -142,8 +142,10 @@ class FusedUpdate:
         W, me, st = self.world, self.rank, self.recv_stride
         local = self.block.peer_ptrs("grad")[me]
         peers = self.block.peer_ptrs("recv")
-        deltas = [peers[p] + ((par * W + me) * st) * 4 - local for par in range(2) for p in range(W)]
-        return dict(push_deltas=deltas, push_me=me, push_mask=mask, push_state=self.state)
+        if getattr(self, "_push_table", None) is None:
+            deltas = [peers[p] + ((par * W + me) * st) * 4 - local for par in range(2) for p in range(W)]
+            self._push_table = torch.tensor(deltas, dtype=torch.int64, device=self.device)
+        return dict(push_table=self._push_table, push_me=me, push_mask=mask, push_state=self.state)
 
     # StepState accessors (int32 view: epoch, blocks_done, step(lo,hi), iter(lo,hi), stopped, ...)
     def iters_done(self) -> int:

@@ -249,9 +249,9 @@ class FusedCNN:
             else:
                 self.bias[id(m)] = None
                 self.gb[id(m)] = None
-            peer = getattr(self.fu, "peer_param_ptrs", None)
-            self.peer_kw[id(m)] = dict(peer_ptrs=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo, peer_bias_off=bo,
-                                       peer_fill_local=True) if peer else {}
+            peer = getattr(self.fu, "peer_table", None)
+            self.peer_kw[id(m)] = dict(peer_table=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo, peer_bias_off=bo,
+                                       peer_fill_local=True) if peer is not None else {}
         if backend_factory is None:
             self.fu.build([seg_of[o] for o in sorted(seg_of)], zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]

@@ -199,9 +199,9 @@ class FusedMLP:
             else:
                 self.bias.append(None)
                 self.gb.append(None)
-            peer = getattr(self.fu, "peer_param_ptrs", None)
-            if peer:
-                self.peer_kw.append(dict(peer_ptrs=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo,
+            peer = getattr(self.fu, "peer_table", None)
+            if peer is not None:
+                self.peer_kw.append(dict(peer_table=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo,
                                          peer_bias_off=bo, peer_fill_local=True))
             else:
                 self.peer_kw.append({})

@@ -488,7 +488,7 @@ def test_gemm_k_ag_gathers_weights_from_sharded_fp32_arena(C):
     x = _mk(Bt, I, 0.2, 60)
     y = torch.zeros(Bt, O, dtype=torch.bfloat16, device=dev())
     wb = torch.zeros(O, I, dtype=torch.bfloat16, device=dev())
-    C.gemm_bf16(x, False, wb, False, Bt, O, I, relu=True, out_bf16=y, peer_ptrs=[o.data_ptr() for o in owners],
+    C.gemm_bf16(x, False, wb, False, Bt, O, I, relu=True, out_bf16=y, peer_table=torch.tensor([o.data_ptr() for o in owners], dtype=torch.int64, device=dev()),
                 peer_shard_elems=shard, peer_w_off=w_off, peer_bias_off=b_off, peer_fill_local=True)
     ref = torch.relu(x.float() @ W.to(torch.bfloat16).float().t() + bias)
     torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
@@ -503,7 +503,7 @@ def test_gemm_k_ag_gathers_weights_from_sharded_fp32_arena(C):
     loss = torch.zeros(1, device=dev())
     wb2 = torch.zeros(O2, 256, dtype=torch.bfloat16, device=dev())[:, :I2]
     C.gemm_bf16(a, False, wb2, False, Bt, O2, I2, loss_kind=1, labels=labels, loss_slot=loss, loss_scale=1.0 / Bt,
-                peer_ptrs=[o.data_ptr() for o in owners2], peer_shard_elems=sh2, peer_w_off=64, peer_bias_off=3008)
+                peer_table=torch.tensor([o.data_ptr() for o in owners2], dtype=torch.int64, device=dev()), peer_shard_elems=sh2, peer_w_off=64, peer_bias_off=3008)
     W2 = flat2[64:64 + O2 * I2].view(O2, I2).to(torch.bfloat16).float()
     ref2 = torch.nn.functional.cross_entropy(a.float() @ W2.t() + flat2[3008:3008 + O2], labels.long())
     torch.testing.assert_close(loss[0], ref2, rtol=1e-3, atol=1e-3)
