@@ -127,7 +127,7 @@ def run_reference(args):
     est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
                      iters=args.warmup + args.steps + 1, verbose=0, mode="synchronous", device=args.device,
                      miniBatch=-1, earlyStopPatience=-1)
-    clocks = ClockSampler(20, list(range(args.gpus))).start()
+    clocks = ClockSampler(int(os.environ.get("SPARKTORCH_CLOCK_PERIOD_MS", "100")), list(range(args.gpus))).start()
     t0 = time.time()
     est.fit(df)
     fit_s = time.time() - t0
@@ -188,7 +188,10 @@ def run_ours(args):
         est._time_window = (args.warmup, args.steps)
         return est.fit(df).getTrainingHistory()
 
-    clocks = ClockSampler(20, list(range(args.gpus))).start()
+    period = int(os.environ.get("SPARKTORCH_CLOCK_PERIOD_MS", "100"))
+    clocks = ClockSampler(max(period, 5), list(range(args.gpus)))
+    if period > 0:
+        clocks.start()
     h = fit(streaming=False)
     he = None if (args.no_e2e or args.mode == "hogwild") else fit(streaming=True)
     time.sleep(0.15)
@@ -199,7 +202,7 @@ def run_ours(args):
         lo, hi = clocks.window(w["host_t0"], w["host_t1"])
         out = clocks.summary(lo, hi)
         out["window_s"] = round(w["host_t1"] - w["host_t0"], 4)
-        out["note"] = "nvidia-smi samples (20 ms period) taken during the timed window +-0.12 s"
+        out["note"] = f"nvidia-smi samples ({period} ms period) taken during the timed window +-0.12 s"
         return out
 
     gb = args.batch * args.gpus
