@@ -42,21 +42,6 @@ struct GemmSmem {
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-// Mirror a gradient-arena write to the peers (see GemmEpilogue::push_*).
-ST_DEVINL void push_store_f32(const GemmEpilogue& ep, int par, float* local, float v, bool atomic) {
-  for (int p = 0; p < ep.push_world; ++p) {
-    if (p == ep.push_me) continue;
-    float* q = reinterpret_cast<float*>(reinterpret_cast<char*>(local) + ep.push_delta[par * ep.push_world + p]);
-    if (atomic) red_add_f32(q, v); else *q = v;
-  }
-}
-ST_DEVINL void push_store_f4(const GemmEpilogue& ep, int par, float4* local, const float4& v) {
-  for (int p = 0; p < ep.push_world; ++p) {
-    if (p == ep.push_me) continue;
-    *reinterpret_cast<float4*>(reinterpret_cast<char*>(local) + ep.push_delta[par * ep.push_world + p]) = v;
-  }
-}
-
 // One 32x(CHUNK) slab of the accumulator (thread = row, registers = columns): fused epilogue math and stores.
 // Shared by the single-tile and the persistent kernel.
 template <int CHUNK>
@@ -64,8 +49,7 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
                               const __nv_bfloat16* mrow, bool have_bias, const float* s_bias, int c0, int row, bool row_ok,
                               int col0, int N, int lane, int lbl_off) {
   const bool vec_ok = (col0 + CHUNK <= N);   // leading dims are multiples of 8 elements, col0 multiple of 16
-  const int par = (ep.push_world > 0 && ep.push_state != nullptr) ? int(ep.push_state->iter & 1) : 0;
-  const bool push_f32 = ep.push_world > 1 && (ep.push_mask & 1);
+  float loss_part = 0.f, colsum_part = 0.f;     // what this thread added to the loss slot / its bias-gradient column
   float acc[32];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
@@ -118,10 +102,8 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
     for (int j = 0; j < CHUNK; ++j) acc[j] = (row_ok && j < N) ? (acc[j] * inv - (j == y ? 1.f : 0.f)) * ep.loss_scale : 0.f;
 #pragma unroll
     for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-    if (lane == 0) {
-      red_add_f32(ep.loss_slot, li * ep.loss_scale);
-      if (ep.push_world > 1 && (ep.push_mask & 4)) push_store_f32(ep, par, ep.loss_slot, li * ep.loss_scale, true);
-    }
+    loss_part = li * ep.loss_scale;
+    if (lane == 0) red_add_f32(ep.loss_slot, loss_part);
   } else if (ep.loss_kind == 2) {   // mean squared error over M x N
     float li = 0.f;
 #pragma unroll
@@ -133,10 +115,8 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-    if (lane == 0) {
-      red_add_f32(ep.loss_slot, li * ep.loss_scale);
-      if (ep.push_world > 1 && (ep.push_mask & 4)) push_store_f32(ep, par, ep.loss_slot, li * ep.loss_scale, true);
-    }
+    loss_part = li * ep.loss_scale;
+    if (lane == 0) red_add_f32(ep.loss_slot, loss_part);
   }
   if (!row_ok) {
 #pragma unroll
@@ -168,24 +148,15 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
     if (ep.atomic_f32) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        if (col0 + j < N) {
-          red_add_f32(op + j, acc[j]);
-          if (push_f32) push_store_f32(ep, par, op + j, acc[j], true);
-        }
+        if (col0 + j < N) red_add_f32(op + j, acc[j]);
     } else if (vec_ok && (ep.ld_f32 & 3) == 0) {
 #pragma unroll
-      for (int v = 0; v < CHUNK / 4; ++v) {
-        const float4 w = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
-        reinterpret_cast<float4*>(op)[v] = w;
-        if (push_f32) push_store_f4(ep, par, reinterpret_cast<float4*>(op) + v, w);
-      }
+      for (int v = 0; v < CHUNK / 4; ++v)
+        reinterpret_cast<float4*>(op)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
     } else {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        if (col0 + j < N) {
-          op[j] = acc[j];
-          if (push_f32) push_store_f32(ep, par, op + j, acc[j], false);
-        }
+        if (col0 + j < N) op[j] = acc[j];
     }
   }
   // ---- transposed stores: lanes hold consecutive rows -> coalesced along m
@@ -201,7 +172,6 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
       if (col0 + j < N && row_ok) {
         float* op = ep.out_t_f32 + size_t(col0 + j) * ep.ld_f32_t + row;
         if (ep.atomic_f32) red_add_f32(op, acc[j]); else *op = acc[j];
-        if (push_f32) push_store_f32(ep, par, op, acc[j], ep.atomic_f32 != 0);
       }
     }
   }
@@ -221,9 +191,44 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
       }
     }
-    if (lane < CHUNK && col0 + lane < N) {
-      red_add_f32(ep.colsum + col0 + lane, v[0]);
-      if (ep.push_world > 1 && (ep.push_mask & 2)) push_store_f32(ep, par, ep.colsum + col0 + lane, v[0], true);
+    colsum_part = v[0];
+    if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, colsum_part);
+  }
+  // ---- GEMM -> all-gather push (one warp-uniform branch; nothing of this is issued on the normal path):
+  //      repeat every write that went into the LOCAL gradient arena into my receive slot on each peer.
+  if (ep.push_world > 1 && ep.push_mask != 0) {
+    const int par = int(ep.push_state->iter & 1);
+    for (int p = 0; p < ep.push_world; ++p) {
+      if (p == ep.push_me) continue;
+      const long long delta = ep.push_delta[par * ep.push_world + p];
+      if ((ep.push_mask & 1) && ep.out_f32 != nullptr && row_ok && ep.loss_kind == 0) {
+        float* op = reinterpret_cast<float*>(reinterpret_cast<char*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col0) + delta);
+        if (ep.atomic_f32) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) red_add_f32(op + j, acc[j]);
+        } else if (vec_ok && (ep.ld_f32 & 3) == 0) {
+#pragma unroll
+          for (int v = 0; v < CHUNK / 4; ++v)
+            reinterpret_cast<float4*>(op)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j)
+            if (col0 + j < N) op[j] = acc[j];
+        }
+      }
+      if ((ep.push_mask & 1) && ep.out_t_f32 != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j)
+          if (col0 + j < N) {
+            float* op = reinterpret_cast<float*>(reinterpret_cast<char*>(ep.out_t_f32 + size_t(col0 + j) * ep.ld_f32_t + row) + delta);
+            if (ep.atomic_f32) red_add_f32(op, acc[j]); else *op = acc[j];
+          }
+      }
+      if ((ep.push_mask & 2) && ep.colsum != nullptr && lane < CHUNK && col0 + lane < N)
+        red_add_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(ep.colsum + col0 + lane) + delta), colsum_part);
+      if ((ep.push_mask & 4) && ep.loss_kind != 0 && lane == 0)
+        red_add_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(ep.loss_slot) + delta), loss_part);
     }
   }
 }

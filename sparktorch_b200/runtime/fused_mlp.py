@@ -174,9 +174,13 @@ class FusedMLP:
         if backend_factory is not None:      # hogwild: owner-sharded parameters, K-AG forward, remote-apply push
             self.fu = backend_factory(numel, off)
         else:
-            # small arenas: one-shot exchange, gradients pushed to the peers by the GEMM epilogues themselves
-            want = os.environ.get("SPARKTORCH_EXCHANGE", "auto")
-            push = world > 1 and fuse_loss and (want == "push" or (want == "auto" and numel * 4 <= (8 << 20)))
+            # Default: two-shot K-AR (owner reduces, publishes -> every replica holds bit-identical parameters and takes
+            # the same early-stop decision).  SPARKTORCH_EXCHANGE=push opts into the one-shot exchange where the GEMM
+            # epilogues mirror their gradient writes into receive slots on every peer: one barrier less, but the
+            # mirrored fp32 atomics land in a different order per copy, so replicas agree only to rounding - it is
+            # therefore never combined with early stopping (a split stop vote would dead-lock the barrier).
+            want = os.environ.get("SPARKTORCH_EXCHANGE", "twoshot")
+            push = world > 1 and fuse_loss and want == "push" and patience == 0
             self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off,
                                   exchange="push" if push else "twoshot")
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)

@@ -110,6 +110,21 @@ def main():
     dist.all_gather(gathered, losses)
     for gl in gathered:
         assert torch.equal(gl, gathered[0]), "ranks disagree on the distributed loss history"
+    # one-shot push exchange (opt-in): replicas agree to rounding, training converges the same way
+    os.environ["SPARKTORCH_EXCHANGE"] = "push"
+    try:
+        torch.manual_seed(1234 + rank)
+        resp = train_partition(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y,
+                               TrainConfig(iters=120, mini_batch=256, device="cuda", seed=5, engine="fused"), dev)
+    finally:
+        os.environ.pop("SPARKTORCH_EXCHANGE", None)
+    assert resp.history["comm"] == "P2PPush", resp.history["comm"]
+    lp = torch.tensor(resp.history["train_loss"], device=dev)
+    gp = [torch.zeros_like(lp) for _ in range(world)]
+    dist.all_gather(gp, lp)
+    for g in gp:
+        assert torch.allclose(g, gp[0], rtol=1e-3, atol=1e-4), "push exchange: ranks drifted apart"
+    assert torch.allclose(lp, losses, rtol=5e-2, atol=5e-3), (lp[-5:], losses[-5:])
     cfg = TrainConfig(iters=40, mini_batch=256, device="cuda", seed=5, engine="fused", early_stop_patience=2)
     res = train_partition(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.SGD, {"lr": 0.0}, X, Y, cfg, dev)
     stops = torch.tensor([res.history["stopped_at"] if res.history["stopped_at"] is not None else -1], device=dev)
