@@ -56,10 +56,15 @@ def main():
     while size <= max_bytes:
         n = size // 4
         iters = 200 if size <= (1 << 20) else (40 if size <= (1 << 26) else 10)
-        ours = timed(lambda: C.allreduce_sum(blk.peer_ptrs("buf"), blk.peer_ptrs("flags"), state, world, rank, n), iters, dev)
+        p2p = timed(lambda: C.allreduce_sum(blk.peer_ptrs("buf"), blk.peer_ptrs("flags"), state, world, rank, n), iters, dev)
+        mc = blk.multicast_ptr("buf")
+        nvls = timed(lambda: C.allreduce_sum(blk.peer_ptrs("buf"), blk.peer_ptrs("flags"), state, world, rank, n, mc), iters,
+                     dev) if mc else float("inf")
+        ours = min(p2p, nvls)
         nccl = timed(lambda: dist.all_reduce(nccl_buf[:n]), iters, dev)
         bus = 2 * (world - 1) / world * size
-        rec = {"bytes": size, "ours_us": ours * 1e3, "nccl_us": nccl * 1e3, "ours_busbw_GBs": bus / ours / 1e6,
+        rec = {"bytes": size, "ours_us": ours * 1e3, "nccl_us": nccl * 1e3, "ours_p2p_us": p2p * 1e3,
+               "ours_nvls_us": nvls * 1e3 if mc else None, "ours_busbw_GBs": bus / ours / 1e6,
                "nccl_busbw_GBs": bus / nccl / 1e6}
         out.append(rec)
         if rank == 0:

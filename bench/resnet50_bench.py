@@ -1,10 +1,11 @@
 """ResNet-50 (lazy envelope, synthetic 3x224x224 rows) through SparkTorch.fit on N GPUs.
 
-Convolutions of this model still run on cuDNN via the eager engine (bf16 autocast); the gradient
-exchange + optimizer is our fused K-AR kernel (two-shot NVLink reduce-scatter + Adam + publish, 102 MB fp32
-arena).  The fp8 block-scaled tcgen05 conv path named in BASELINE.json is future work.
+--engine fused (default): every convolution is a tcgen05 GEMM over channels-last bf16 activations, batch-norm /
+pooling / loss are the kernels of csrc/norm.cu, the whole step is one CUDA graph and the gradient exchange +
+optimizer is the fused K-AR kernel (runtime/fused_resnet.py).  --engine eager: torch autograd with cuDNN
+convolutions under bf16 autocast + the same K-AR kernel (the library baseline on the same box).
 
-    python bench/resnet50_bench.py --gpus 1 --steps 10 --warmup 3 [--batch 32] [--impl ours|reference]
+    python bench/resnet50_bench.py --gpus 1 --steps 10 --warmup 3 [--batch 32] [--engine fused|eager]
     python -m torch.distributed.run --nproc-per-node 8 ... bench/resnet50_bench.py --gpus 8
 """
 import argparse
@@ -23,6 +24,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--engine", default="fused")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -42,13 +44,14 @@ def main():
     obj = serialize_torch_obj_lazy(ResNet50, nn.CrossEntropyLoss, torch.optim.SGD, {"lr": 0.1, "momentum": 0.9},
                                    {"num_classes": 1000, "image_size": a.image})
     est = SparkTorch(inputCol="features", labelCol="label", predictionCol="p", torchObj=obj, iters=a.warmup + a.steps,
-                     device="cuda", precision="bf16", engine="eager", seed=0)
+                     device="cuda", precision="bf16", engine=a.engine, seed=0)
     est._time_window = (a.warmup, a.steps)
     h = est.fit(df).getTrainingHistory()
     ms = h["window_ms"]["device_ms"]
     print(json.dumps({"metric": "ResNet-50 samples/sec (whole job)", "value": n * a.steps / (ms / 1e3), "unit": "samples/s",
                       "n_gpus": a.gpus, "ms_per_step": ms / a.steps, "global_batch": n, "engine": h["engine"], "comm": h["comm"],
-                      "dtype": "bf16 autocast (cuDNN convs) + fp32 master/K-AR", "data": "synthetic"}), flush=True)
+                      "gpu_launches_per_step": h.get("gpu_launches_per_step"),
+                      "dtype": "bf16 activations/weights, fp32 accumulate + fp32 master/K-AR", "data": "synthetic"}), flush=True)
     spark.stop()
 
 

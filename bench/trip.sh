@@ -1,17 +1,28 @@
+# usage: bash bench/trip.sh N   – multi-GPU validation + scaling numbers on one box
+N=${1:-4}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name --format=csv,noheader | head -2
-bash bench/gpu_ci.sh 2>&1 | tail -30
-echo "=== ours n1 x2"
-for i in 1 2; do timeout 300 python bench.py --gpus 1 --steps 2000 --warmup 50 2>&1 | tail -1; done
-echo "=== multi_gpu_check"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multi_gpu_check.py > gpurun_out/mgc.log 2>&1; echo rc=$?; tail -25 gpurun_out/mgc.log
-echo "=== ours n2 push"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 2000 --warmup 50 2>&1 | tail -1
-echo "=== ours n2 twoshot"
-SPARKTORCH_EXCHANGE=twoshot timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --steps 2000 --warmup 50 2>&1 | tail -1
-echo "=== cnn n1"
-timeout 300 python bench.py --gpus 1 --steps 500 --warmup 20 --model cnn 2>&1 | tail -1
-echo "=== cnn n2"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus 2 --steps 500 --warmup 20 --model cnn 2>&1 | tail -1
-echo "=== hogwild n2 dnn"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29615 bench.py --gpus 2 --steps 1000 --warmup 50 --mode hogwild 2>&1 | tail -1
+nvidia-smi --query-gpu=name --format=csv,noheader | head -8 | sort | uniq -c
+nvidia-smi topo -m 2>/dev/null | head -12 > gpurun_out/topo_n$N.txt
+tr() { port=$1; shift; timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port "$@"; }
+echo "=== multi_gpu_check N=$N"
+tr 29611 tests/multi_gpu_check.py > gpurun_out/mgc_n$N.log 2>&1; echo rc=$?; grep -E "OK|Error|assert" gpurun_out/mgc_n$N.log | head -8
+echo "=== pytest test_gpu_multi"
+timeout 600 python -m pytest -m gpu -q -p no:cacheprovider tests/test_gpu_multi.py > gpurun_out/ci_multi_n$N.log 2>&1; echo rc=$?; tail -3 gpurun_out/ci_multi_n$N.log
+echo "=== reference dnn N=$N"
+tr 29612 bench.py --impl reference --gpus $N --steps 300 --warmup 20 2>&1 | tail -1 | tee gpurun_out/ref_dnn_n$N.json | cut -c1-400
+echo "=== ours dnn N=$N"
+tr 29613 bench.py --gpus $N --steps 2000 --warmup 50 2>&1 | tail -1 | tee gpurun_out/ours_dnn_n$N.json | cut -c1-400
+echo "=== ours dnn N=1 (same box)"
+timeout 300 python bench.py --gpus 1 --steps 2000 --warmup 50 2>&1 | tail -1 | tee gpurun_out/ours_dnn_n1_box$N.json | cut -c1-300
+echo "=== reference cnn N=$N"
+tr 29614 bench.py --impl reference --model cnn --gpus $N --steps 200 --warmup 20 2>&1 | tail -1 | tee gpurun_out/ref_cnn_n$N.json | cut -c1-400
+echo "=== ours cnn N=$N"
+tr 29615 bench.py --gpus $N --steps 500 --warmup 20 --model cnn 2>&1 | tail -1 | tee gpurun_out/ours_cnn_n$N.json | cut -c1-400
+echo "=== ours cnn hogwild N=$N"
+tr 29616 bench.py --gpus $N --steps 500 --warmup 20 --model cnn --mode hogwild 2>&1 | tail -1 | tee gpurun_out/ours_cnn_hw_n$N.json | cut -c1-400
+echo "=== ours dnn hogwild N=$N"
+tr 29617 bench.py --gpus $N --steps 1000 --warmup 50 --mode hogwild 2>&1 | tail -1 | tee gpurun_out/ours_dnn_hw_n$N.json | cut -c1-400
+echo "=== allreduce sweep N=$N"
+tr 29618 bench/allreduce_sweep.py > gpurun_out/ar_sweep_n$N.log 2>&1; echo rc=$?; tail -24 gpurun_out/ar_sweep_n$N.log
+echo "=== kar profile N=$N"
+tr 29619 bench/kar_profile.py > gpurun_out/kar_n$N.log 2>&1; echo rc=$?; tail -12 gpurun_out/kar_n$N.log

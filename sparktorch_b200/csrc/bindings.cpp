@@ -196,6 +196,131 @@ void maxpool_dropout(bool backward, const Tensor& x_or_dx, int64_t ld_x, const T
   }
 }
 
+// ------------------------------------------------------------------ residual conv nets (norm.cu)
+static const __nv_bfloat16* bfo(const OptT& t) { return t ? bf16p(*t) : nullptr; }
+static int64_t ldo(const OptT& t) { return t ? t->stride(0) : 0; }
+
+void im2col_cl(const Tensor& x, int64_t B, int64_t H, int64_t W, int64_t Cc, int64_t kh, int64_t kw, int64_t stride, int64_t pad,
+               int64_t dil, int64_t OH, int64_t OW, const Tensor& col) {
+  req_2d(x, at::kBFloat16, "x");
+  req_2d(col, at::kBFloat16, "col");
+  c10::cuda::CUDAGuard guard(x.device());
+  st::Im2colClArgs a{};
+  a.x = bf16p(x); a.ld_x = x.stride(0);
+  a.B = int(B); a.H = int(H); a.W = int(W); a.C = int(Cc); a.kh = int(kh); a.kw = int(kw);
+  a.stride = int(stride); a.pad = int(pad); a.dil = int(dil < 1 ? 1 : dil); a.OH = int(OH); a.OW = int(OW);
+  a.col = bf16pm(col); a.ld_col = col.stride(0);
+  TORCH_CHECK(x.size(0) >= B * H * W && x.size(1) >= Cc, "im2col_cl: x too small");
+  TORCH_CHECK(col.size(0) >= B * OH * OW && col.size(1) >= kh * kw * Cc, "im2col_cl: col too small");
+  check(st::im2col_cl(a, cur_stream()), "im2col_cl");
+}
+
+void flip_conv_weight_cl(const Tensor& w, int64_t Cout, int64_t Cin, int64_t kh, int64_t kw, const Tensor& out) {
+  req_2d(w, at::kBFloat16, "w");
+  req_2d(out, at::kBFloat16, "out");
+  TORCH_CHECK(w.size(0) >= Cout && w.size(1) >= kh * kw * Cin && out.size(0) >= Cin && out.size(1) >= kh * kw * Cout);
+  c10::cuda::CUDAGuard guard(w.device());
+  check(st::flip_conv_weight_cl(bf16p(w), w.stride(0), int(Cout), int(Cin), int(kh), int(kw), bf16pm(out), out.stride(0), cur_stream()),
+        "flip_conv_weight_cl");
+}
+
+void bn_stats(const Tensor& y, int64_t M, int64_t Cc, const Tensor& sums) {
+  req_2d(y, at::kBFloat16, "y");
+  TORCH_CHECK(sums.scalar_type() == at::kFloat && sums.numel() >= 2 * Cc && y.size(0) >= M && y.size(1) >= Cc);
+  c10::cuda::CUDAGuard guard(y.device());
+  check(st::bn_stats(bf16p(y), y.stride(0), M, int(Cc), sums.data_ptr<float>(), cur_stream()), "bn_stats");
+}
+
+void bn_finalize(const Tensor& sums, int64_t M, int64_t Cc, double eps, double momentum, const OptT& running_mean,
+                 const OptT& running_var, const Tensor& stats, bool from_running, bool update_running) {
+  TORCH_CHECK(sums.scalar_type() == at::kFloat && stats.scalar_type() == at::kFloat && stats.numel() >= 2 * Cc);
+  if (running_mean) TORCH_CHECK(running_mean->scalar_type() == at::kFloat && running_var->scalar_type() == at::kFloat &&
+                                running_mean->is_contiguous() && running_var->is_contiguous() && running_mean->numel() >= Cc);
+  TORCH_CHECK(!from_running || running_mean.has_value());
+  c10::cuda::CUDAGuard guard(sums.device());
+  check(st::bn_finalize(sums.data_ptr<float>(), M, int(Cc), float(eps), float(momentum),
+                        running_mean ? running_mean->data_ptr<float>() : nullptr, running_var ? running_var->data_ptr<float>() : nullptr,
+                        stats.data_ptr<float>(), from_running, update_running, cur_stream()), "bn_finalize");
+}
+
+static st::BnArgs bn_args(int64_t M, int64_t Cc, bool relu, const Tensor& y, const Tensor& z, const Tensor& stats, const Tensor& gamma) {
+  req_2d(y, at::kBFloat16, "y");
+  req_2d(z, at::kBFloat16, "z");
+  TORCH_CHECK(y.size(0) >= M && y.size(1) >= Cc && z.size(0) >= M && z.size(1) >= Cc && stats.numel() >= 2 * Cc && gamma.numel() >= Cc);
+  TORCH_CHECK(stats.scalar_type() == at::kFloat && gamma.scalar_type() == at::kFloat);
+  st::BnArgs a{};
+  a.M = M; a.C = int(Cc); a.relu = relu;
+  a.y = bf16p(y); a.ld = y.stride(0);
+  a.z = bf16pm(z); a.ld_z = z.stride(0);
+  a.stats = stats.data_ptr<float>();
+  a.gamma = gamma.data_ptr<float>();
+  return a;
+}
+
+void bn_apply(const Tensor& y, int64_t M, int64_t Cc, const Tensor& stats, const Tensor& gamma, const Tensor& beta, const Tensor& z,
+              bool relu, const OptT& residual) {
+  c10::cuda::CUDAGuard guard(y.device());
+  st::BnArgs a = bn_args(M, Cc, relu, y, z, stats, gamma);
+  TORCH_CHECK(beta.scalar_type() == at::kFloat && beta.numel() >= Cc);
+  a.beta = beta.data_ptr<float>();
+  if (residual) { req_2d(*residual, at::kBFloat16, "residual"); TORCH_CHECK(residual->size(0) >= M && residual->size(1) >= Cc); }
+  a.residual = bfo(residual); a.ld_res = ldo(residual);
+  check(st::bn_apply(a, cur_stream()), "bn_apply");
+}
+
+// reduce=true: dgamma/dbeta += ...;  reduce=false: dy (and g_out) from the finished dgamma/dbeta
+void bn_backward(bool reduce, const Tensor& y, int64_t M, int64_t Cc, const Tensor& stats, const Tensor& gamma, const Tensor& z,
+                 bool relu, const Tensor& dz_a, const OptT& dz_b, const Tensor& dgamma, const Tensor& dbeta, const OptT& dy,
+                 const OptT& g_out) {
+  c10::cuda::CUDAGuard guard(y.device());
+  st::BnArgs a = bn_args(M, Cc, relu, y, z, stats, gamma);
+  req_2d(dz_a, at::kBFloat16, "dz_a");
+  TORCH_CHECK(dz_a.size(0) >= M && dz_a.size(1) >= Cc);
+  a.dz_a = bf16p(dz_a); a.ld_dz = dz_a.stride(0);
+  if (dz_b) { req_2d(*dz_b, at::kBFloat16, "dz_b"); TORCH_CHECK(dz_b->stride(0) == dz_a.stride(0) && dz_b->size(0) >= M, "dz_b pitch"); a.dz_b = bf16p(*dz_b); }
+  TORCH_CHECK(dgamma.scalar_type() == at::kFloat && dbeta.scalar_type() == at::kFloat && dgamma.numel() >= Cc && dbeta.numel() >= Cc);
+  a.dgamma = dgamma.data_ptr<float>(); a.dbeta = dbeta.data_ptr<float>();
+  if (reduce) {
+    check(st::bn_bwd_reduce(a, cur_stream()), "bn_bwd_reduce");
+  } else {
+    TORCH_CHECK(dy.has_value());
+    req_2d(*dy, at::kBFloat16, "dy");
+    TORCH_CHECK(dy->size(0) >= M && dy->size(1) >= Cc);
+    a.dy = bf16pm(*dy); a.ld_dy = dy->stride(0);
+    if (g_out) { req_2d(*g_out, at::kBFloat16, "g_out"); TORCH_CHECK(g_out->stride(0) == dz_a.stride(0) && g_out->size(0) >= M, "g_out pitch"); a.g_out = bf16pm(*g_out); }
+    check(st::bn_bwd_apply(a, cur_stream()), "bn_bwd_apply");
+  }
+}
+
+void maxpool_cl(bool backward, const Tensor& x_or_dx, const Tensor& y_or_dy, const Tensor& idx, int64_t B, int64_t H, int64_t W,
+                int64_t Cc, int64_t k, int64_t s, int64_t p, const OptT& dy_b) {
+  req_2d(x_or_dx, at::kBFloat16, "x");
+  req_2d(y_or_dy, at::kBFloat16, "y");
+  TORCH_CHECK(idx.scalar_type() == at::kByte);
+  c10::cuda::CUDAGuard guard(x_or_dx.device());
+  st::Pool2Args a{};
+  a.B = int(B); a.H = int(H); a.W = int(W); a.C = int(Cc); a.k = int(k); a.s = int(s); a.p = int(p);
+  a.PH = int((H + 2 * p - k) / s + 1); a.PW = int((W + 2 * p - k) / s + 1);
+  TORCH_CHECK(x_or_dx.size(0) >= B * H * W && y_or_dy.size(0) >= B * a.PH * a.PW && idx.numel() >= B * a.PH * a.PW * Cc);
+  a.ld_x = x_or_dx.stride(0); a.ld_y = y_or_dy.stride(0);
+  a.idx = idx.data_ptr<uint8_t>();
+  if (!backward) { a.x = bf16p(x_or_dx); a.y = bf16pm(y_or_dy); }
+  else {
+    a.dx = bf16pm(x_or_dx); a.dy = bf16p(y_or_dy);
+    if (dy_b) { req_2d(*dy_b, at::kBFloat16, "dy_b"); TORCH_CHECK(dy_b->stride(0) == y_or_dy.stride(0) && dy_b->size(0) >= B * a.PH * a.PW); a.dy_b = bf16p(*dy_b); }
+  }
+  check(st::maxpool_cl(a, backward, cur_stream()), "maxpool_cl");
+}
+
+void avgpool_cl(bool backward, const Tensor& x_or_dx, const Tensor& y_or_dy, int64_t B, int64_t HW, int64_t Cc) {
+  req_2d(x_or_dx, at::kBFloat16, "x");
+  req_2d(y_or_dy, at::kBFloat16, "y");
+  TORCH_CHECK(x_or_dx.size(0) >= B * HW && y_or_dy.size(0) >= B && x_or_dx.size(1) >= Cc && y_or_dy.size(1) >= Cc);
+  c10::cuda::CUDAGuard guard(x_or_dx.device());
+  check(st::avgpool_cl(bf16pm(x_or_dx), x_or_dx.stride(0), bf16pm(y_or_dy), y_or_dy.stride(0), int(B), int(HW), int(Cc), backward,
+                       cur_stream()), "avgpool_cl");
+}
+
 // ------------------------------------------------------------------ fused all-reduce + optimizer
 class Updater {
  public:
@@ -246,11 +371,12 @@ class Updater {
 };
 
 void allreduce_sum(std::vector<int64_t> buf_ptrs, std::vector<int64_t> flag_ptrs, const Tensor& state, int64_t world,
-                   int64_t rank, int64_t n) {
+                   int64_t rank, int64_t n, int64_t multicast_ptr) {
   float* bufs[8];
   uint32_t* flags[8];
   for (int r = 0; r < world; ++r) { bufs[r] = reinterpret_cast<float*>(buf_ptrs[r]); flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]); }
-  check(st::allreduce_sum_f32(bufs, flags, reinterpret_cast<st::StepState*>(state.data_ptr()), int(world), int(rank), n, 1, cur_stream()),
+  check(st::allreduce_sum_f32(bufs, flags, reinterpret_cast<st::StepState*>(state.data_ptr()), int(world), int(rank), n,
+                              reinterpret_cast<float*>(multicast_ptr), cur_stream()),
         "allreduce_sum");
 }
 
@@ -430,7 +556,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("idx"), py::arg("B"), py::arg("H"), py::arg("W"), py::arg("C"), py::arg("k"), py::arg("p_drop") = 0.0,
         py::arg("train") = false, py::arg("seed") = 0, py::arg("state") = py::none(), py::arg("y_nhwc") = false,
         py::arg("relu_x") = py::none(), py::arg("db") = py::none());
-  m.def("allreduce_sum", &allreduce_sum);
+  m.def("im2col_cl", &im2col_cl);
+  m.def("flip_conv_weight_cl", &flip_conv_weight_cl);
+  m.def("bn_stats", &bn_stats);
+  m.def("bn_finalize", &bn_finalize, py::arg("sums"), py::arg("M"), py::arg("C"), py::arg("eps"), py::arg("momentum"),
+        py::arg("running_mean") = py::none(), py::arg("running_var") = py::none(), py::arg("stats"),
+        py::arg("from_running") = false, py::arg("update_running") = true);
+  m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("M"), py::arg("C"), py::arg("stats"), py::arg("gamma"), py::arg("beta"),
+        py::arg("z"), py::arg("relu") = false, py::arg("residual") = py::none());
+  m.def("bn_backward", &bn_backward, py::arg("reduce"), py::arg("y"), py::arg("M"), py::arg("C"), py::arg("stats"), py::arg("gamma"),
+        py::arg("z"), py::arg("relu"), py::arg("dz_a"), py::arg("dz_b") = py::none(), py::arg("dgamma"), py::arg("dbeta"),
+        py::arg("dy") = py::none(), py::arg("g_out") = py::none());
+  m.def("maxpool_cl", &maxpool_cl, py::arg("backward"), py::arg("x_or_dx"), py::arg("y_or_dy"), py::arg("idx"), py::arg("B"),
+        py::arg("H"), py::arg("W"), py::arg("C"), py::arg("k"), py::arg("s"), py::arg("p"), py::arg("dy_b") = py::none());
+  m.def("avgpool_cl", &avgpool_cl);
+  m.def("allreduce_sum", &allreduce_sum, py::arg("buf_ptrs"), py::arg("flag_ptrs"), py::arg("state"), py::arg("world"),
+        py::arg("rank"), py::arg("n"), py::arg("multicast_ptr") = 0);
   m.def("pack_segments", &pack_segments);
   m.def("step_state_bytes", &step_state_bytes);
   m.def("set_pdl", &set_pdl);

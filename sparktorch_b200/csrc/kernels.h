@@ -97,7 +97,7 @@ int allreduce_update(const UpdateArgs& a, cudaStream_t stream);
 int allreduce_push_update(const UpdateArgs& a, cudaStream_t stream);   // one-shot: gradients were pushed by the GEMM epilogues
 int publish_params(const UpdateArgs& a, cudaStream_t stream);   // (re)build bf16 copies from fp32 master, no exchange
 int allreduce_sum_f32(float* const* bufs, uint32_t* const* flags, StepState* state, int world, int rank, int64_t n,
-                      int use_twoshot, cudaStream_t stream);
+                      float* multicast, cudaStream_t stream);
 
 // ---- conv.cu
 struct Im2colArgs {
@@ -133,6 +133,59 @@ struct PoolArgs {
 };
 int maxpool_dropout_fwd(const PoolArgs& a, cudaStream_t stream);
 int maxpool_dropout_bwd(const PoolArgs& a, cudaStream_t stream);
+
+// ---- norm.cu (batch norm, channels-last im2col, general pooling: residual conv nets)
+struct Im2colClArgs {
+  const __nv_bfloat16* x;     // NHWC [B, H, W, C], pixel pitch ld_x; C % 8 == 0
+  int64_t ld_x;
+  int B, H, W, C, kh, kw, stride, pad, dil, OH, OW;   // dil: input dilation (zero insertion) for strided dgrad
+  __nv_bfloat16* col;         // [B*OH*OW, ld_col], column (i, j, c)
+  int64_t ld_col;
+};
+int im2col_cl(const Im2colClArgs& a, cudaStream_t stream);
+int flip_conv_weight_cl(const __nv_bfloat16* w, int64_t ld_w, int Cout, int Cin, int kh, int kw, __nv_bfloat16* out, int64_t ld_o,
+                        cudaStream_t stream);
+struct BnArgs {
+  int64_t M;
+  int C, relu;
+  const __nv_bfloat16* y;     // conv output (pre-norm) [M, C]
+  int64_t ld;
+  __nv_bfloat16* z;           // fwd: output; bwd: forward output (ReLU mask)
+  int64_t ld_z;
+  const __nv_bfloat16* residual;
+  int64_t ld_res;
+  const float* stats;         // [2C] mean, rstd
+  const float* gamma;
+  const float* beta;
+  const __nv_bfloat16* dz_a;  // bwd: incoming gradient(s) wrt z
+  const __nv_bfloat16* dz_b;
+  int64_t ld_dz;
+  __nv_bfloat16* dy;          // bwd: gradient wrt y
+  int64_t ld_dy;
+  __nv_bfloat16* g_out;       // bwd: masked incoming gradient (skip connection), pitch ld_dz
+  float* dgamma;              // fp32 gradient arena slots
+  float* dbeta;
+};
+int bn_stats(const __nv_bfloat16* y, int64_t ld, int64_t M, int C, float* sums, cudaStream_t stream);
+int bn_finalize(float* sums, int64_t M, int C, float eps, float momentum, float* running_mean, float* running_var, float* stats,
+                int from_running, int update_running, cudaStream_t stream);
+int bn_apply(const BnArgs& a, cudaStream_t stream);
+int bn_bwd_reduce(const BnArgs& a, cudaStream_t stream);
+int bn_bwd_apply(const BnArgs& a, cudaStream_t stream);
+struct Pool2Args {
+  const __nv_bfloat16* x;     // fwd input NHWC
+  __nv_bfloat16* dx;          // bwd output NHWC
+  int64_t ld_x;
+  __nv_bfloat16* y;           // fwd output NHWC [B, PH, PW, C]
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* dy_b;  // optional second incoming gradient (summed)
+  int64_t ld_y;
+  uint8_t* idx;               // [B, PH, PW, C] argmax tap
+  int B, H, W, C, k, s, p, PH, PW;
+};
+int maxpool_cl(const Pool2Args& a, bool backward, cudaStream_t stream);
+int avgpool_cl(__nv_bfloat16* x_or_dx, int64_t ld_x, __nv_bfloat16* y_or_dy, int64_t ld_y, int B, int HW, int C, bool backward,
+               cudaStream_t stream);
 
 // ---- comm_hw.cu (asynchronous parameter-server mode over peer memory)
 constexpr int HW_MAX_STRIPES = 64;

@@ -180,7 +180,7 @@ class FusedMLP:
             # mirrored fp32 atomics land in a different order per copy, so replicas agree only to rounding - it is
             # therefore never combined with early stopping (a split stop vote would dead-lock the barrier).
             want = os.environ.get("SPARKTORCH_EXCHANGE", "twoshot")
-            push = world > 1 and fuse_loss and want == "push" and patience == 0
+            push = world > 1 and fuse_loss and want == "push" and patience <= 0
             self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off,
                                   exchange="push" if push else "twoshot")
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
@@ -375,12 +375,20 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
 
         lowered = lower_cnn(model, X.shape[1])
         is_cnn = lowered is not None
+    is_resnet = False
+    if lowered is None:
+        from sparktorch_b200.runtime.fused_resnet import lower_resnet
+
+        lowered = lower_resnet(model, X.shape[1])
+        is_resnet = lowered is not None
     if lowered is None:
         return None
     kind = loss_kind(criterion, lowered)
-    if kind is None:
+    if kind is None or (is_resnet and kind != "ce"):
         return None
-    if is_cnn:
+    if is_resnet:
+        d0, dL = X.shape[1], lowered.fc.out_features
+    elif is_cnn:
         d0, dL = X.shape[1], lowered.linears[-1].module.out_features
     else:
         d0, dL = lowered.layers[0].module.in_features, lowered.layers[-1].module.out_features
@@ -414,7 +422,11 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     nv = 0 if x_val is None else x_val.shape[0]
 
     model = model.to(device)
-    if is_cnn:
+    if is_resnet:
+        from sparktorch_b200.runtime.fused_resnet import FusedResNet
+
+        plan = FusedResNet(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1)
+    elif is_cnn:
         from sparktorch_b200.runtime.fused_cnn import FusedCNN
 
         plan = FusedCNN(model, lowered, kind, spec, world, rank, device, Bt, nv, cfg.early_stop_patience, cfg.iters + 1,
@@ -473,12 +485,16 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
 
         # warm-up launch outside capture (module load, smem attributes), then rewind the step state
         p0 = plan.fu.param.clone()
+        if hasattr(plan, "save_extra"):
+            plan.save_extra()                         # e.g. batch-norm running statistics
         if streaming:
             xs[:Bt].copy_(x_host[:Bt].to(device))
             ys[:Bt].copy_(y_host[:Bt].to(device))
         enqueue_step()
         stream.synchronize()
         plan.fu.param.copy_(p0)
+        if hasattr(plan, "restore_extra"):
+            plan.restore_extra()
         for t in (plan.fu.m, plan.fu.v):
             if t is not None:
                 t.zero_()
@@ -554,10 +570,12 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     torch.cuda.synchronize(device)
     t_end = time.time()
     n_done = plan.fu.iters_done()
+    if hasattr(plan, "finish"):
+        plan.finish(n_done)
     stopped = plan.fu.stopped()
     losses = plan.fu.loss_hist[:n_done].cpu().tolist()
     history = {
-        "engine": "fused_cnn" if is_cnn else "fused_mlp",
+        "engine": "fused_resnet" if is_resnet else ("fused_cnn" if is_cnn else "fused_mlp"),
         "comm": ("P2PPush" if getattr(plan.fu, "exchange", "") == "push" else "P2PFused" + ("+NVLS" if plan.fu.use_multicast else "")),
         "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,

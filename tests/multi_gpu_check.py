@@ -49,11 +49,12 @@ def main():
         state = torch.zeros(C.step_state_bytes() // 4, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         dist.barrier()
-        for _ in range(3):                      # repeated launches exercise the epoch protocol
+        for it in range(4):                     # repeated launches exercise the epoch protocol; odd ones go through NVLS
             buf.copy_(src)
             torch.cuda.synchronize()
             dist.barrier()
-            C.allreduce_sum(blk.peer_ptrs("buf"), blk.peer_ptrs("flags"), state, world, rank, n)
+            mc = blk.multicast_ptr("buf") if it % 2 else 0
+            C.allreduce_sum(blk.peer_ptrs("buf"), blk.peer_ptrs("flags"), state, world, rank, n, mc)
             torch.cuda.synchronize()
             torch.testing.assert_close(buf, ref, rtol=1e-5, atol=1e-5)
             dist.barrier()
