@@ -9,4 +9,4 @@ run misc tests/test_gpu_kernels.py -k "not gemm"
 run persist tests/test_gpu_kernels.py -k "persistent"
 run conv tests/test_gpu_kernels.py -k "im2col or conv or maxpool"
 run engine tests/test_gpu_engine.py
-run resnet tests/test_gpu_resnet.py
+run resnet tests/test_gpu_resnet.py tests/test_gpu_norm.py

@@ -37,7 +37,7 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
                double loss_scale, const OptT& win_state, int64_t window_rows, int64_t n_windows, int64_t win_flags,
                const OptT& prof, const OptT& peer_table, int64_t peer_shard_elems, int64_t peer_w_off,
                int64_t peer_bias_off, bool peer_fill_local, const OptT& push_table, int64_t push_me,
-               int64_t push_mask, const OptT& push_state) {
+               int64_t push_mask, const OptT& push_state, const OptT& colsumsq) {
   req_2d(A, at::kBFloat16, "A");
   req_2d(B, at::kBFloat16, "B");
   c10::cuda::CUDAGuard guard(A.device());
@@ -60,6 +60,7 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
   if (out_f32) { req_2d(*out_f32, at::kFloat, "out_f32"); ep.out_f32 = out_f32->data_ptr<float>(); ep.ld_f32 = out_f32->stride(0); }
   if (out_t_f32) { req_2d(*out_t_f32, at::kFloat, "out_t_f32"); ep.out_t_f32 = out_t_f32->data_ptr<float>(); ep.ld_f32_t = out_t_f32->stride(0); }
   if (colsum) { TORCH_CHECK(colsum->scalar_type() == at::kFloat && colsum->numel() >= N); ep.colsum = colsum->data_ptr<float>(); }
+  if (colsumsq) { TORCH_CHECK(colsumsq->scalar_type() == at::kFloat && colsumsq->numel() >= N && !bias.has_value()); ep.colsumsq = colsumsq->data_ptr<float>(); }
   ep.loss_kind = int(loss_kind);
   if (loss_kind != 0) {
     TORCH_CHECK(loss_slot.has_value() && loss_slot->scalar_type() == at::kFloat, "fused loss needs a float loss slot");
@@ -258,9 +259,21 @@ static st::BnArgs bn_args(int64_t M, int64_t Cc, bool relu, const Tensor& y, con
 }
 
 void bn_apply(const Tensor& y, int64_t M, int64_t Cc, const Tensor& stats, const Tensor& gamma, const Tensor& beta, const Tensor& z,
-              bool relu, const OptT& residual) {
+              bool relu, const OptT& residual, const OptT& sums, double eps, double momentum, const OptT& running_mean,
+              const OptT& running_var) {
   c10::cuda::CUDAGuard guard(y.device());
   st::BnArgs a = bn_args(M, Cc, relu, y, z, stats, gamma);
+  if (sums) {            // statistics come straight from the GEMM epilogue's column sums: finalize inline
+    TORCH_CHECK(sums->scalar_type() == at::kFloat && sums->numel() >= 2 * Cc);
+    a.sums = sums->data_ptr<float>();
+    a.stats_out = stats.data_ptr<float>();
+    a.eps = float(eps); a.momentum = float(momentum);
+    if (running_mean) {
+      TORCH_CHECK(running_var.has_value() && running_mean->scalar_type() == at::kFloat && running_var->scalar_type() == at::kFloat &&
+                  running_mean->is_contiguous() && running_var->is_contiguous() && running_mean->numel() >= Cc);
+      a.running_mean = running_mean->data_ptr<float>(); a.running_var = running_var->data_ptr<float>();
+    }
+  }
   TORCH_CHECK(beta.scalar_type() == at::kFloat && beta.numel() >= Cc);
   a.beta = beta.data_ptr<float>();
   if (residual) { req_2d(*residual, at::kBFloat16, "residual"); TORCH_CHECK(residual->size(0) >= M && residual->size(1) >= Cc); }
@@ -543,7 +556,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("prof") = py::none(), py::arg("peer_table") = py::none(), py::arg("peer_shard_elems") = 0,
         py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false,
         py::arg("push_table") = py::none(), py::arg("push_me") = 0, py::arg("push_mask") = 0,
-        py::arg("push_state") = py::none());
+        py::arg("push_state") = py::none(), py::arg("colsumsq") = py::none());
   m.def("softmax_ce", &softmax_ce);
   m.def("mse_loss", &mse_loss);
   m.def("gather_batch", &gather_batch);
@@ -563,7 +576,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("running_mean") = py::none(), py::arg("running_var") = py::none(), py::arg("stats"),
         py::arg("from_running") = false, py::arg("update_running") = true);
   m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("M"), py::arg("C"), py::arg("stats"), py::arg("gamma"), py::arg("beta"),
-        py::arg("z"), py::arg("relu") = false, py::arg("residual") = py::none());
+        py::arg("z"), py::arg("relu") = false, py::arg("residual") = py::none(), py::arg("sums") = py::none(), py::arg("eps") = 1e-5,
+        py::arg("momentum") = 0.1, py::arg("running_mean") = py::none(), py::arg("running_var") = py::none());
   m.def("bn_backward", &bn_backward, py::arg("reduce"), py::arg("y"), py::arg("M"), py::arg("C"), py::arg("stats"), py::arg("gamma"),
         py::arg("z"), py::arg("relu"), py::arg("dz_a"), py::arg("dz_b") = py::none(), py::arg("dgamma"), py::arg("dbeta"),
         py::arg("dy") = py::none(), py::arg("g_out") = py::none());

@@ -194,6 +194,23 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
     colsum_part = v[0];
     if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, colsum_part);
   }
+  // ---- column sums of squares (with colsum: the batch-norm statistics of a convolution output, no extra pass)
+  if (ep.colsumsq != nullptr) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (j < CHUNK) ? acc[j] * acc[j] : 0.f;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float send = up ? v[i] : v[i + s];
+        const float keep = up ? v[i + s] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsumsq + col0 + lane, v[0]);
+  }
   // ---- GEMM -> all-gather push (one warp-uniform branch; nothing of this is issued on the normal path):
   //      repeat every write that went into the LOCAL gradient arena into my receive slot on each peer.
   if (ep.push_world > 1 && ep.push_mask != 0) {

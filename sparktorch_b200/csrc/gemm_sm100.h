@@ -25,6 +25,7 @@ struct GemmEpilogue {
   int64_t ld_f32_t = 0;
   int atomic_f32 = 0;                     // fp32 outputs use red.add (needed for split-K)
   float* colsum = nullptr;                // [N] += sum_m D[m,n]
+  float* colsumsq = nullptr;              // [N] += sum_m D[m,n]^2   (rows >= M contribute 0: no bias on that path)
   // fused loss on the output row (needs N <= 32, one n-tile): 0 none, 1 softmax-CE, 2 MSE.
   // acc becomes dLoss/dOut, so out_bf16 / colsum then emit dZ / db; out_f32 (if set) keeps the raw output.
   int loss_kind = 0;

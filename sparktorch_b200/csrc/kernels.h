@@ -165,6 +165,13 @@ struct BnArgs {
   __nv_bfloat16* g_out;       // bwd: masked incoming gradient (skip connection), pitch ld_dz
   float* dgamma;              // fp32 gradient arena slots
   float* dbeta;
+  // bn_apply with inline finalize: statistics from column sums [2C] (sum, sum of squares) accumulated by the
+  // producing GEMM's epilogue; block 0 stores mean/rstd to stats_out and updates the running statistics
+  const float* sums;
+  float* stats_out;
+  float* running_mean;
+  float* running_var;
+  float eps, momentum;
 };
 int bn_stats(const __nv_bfloat16* y, int64_t ld, int64_t M, int C, float* sums, cudaStream_t stream);
 int bn_finalize(float* sums, int64_t M, int C, float eps, float momentum, float* running_mean, float* running_var, float* stats,

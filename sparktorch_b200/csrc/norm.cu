@@ -43,20 +43,23 @@ ST_DEVINL uint4 pack8(const float* f) {
 __global__ void __launch_bounds__(NT) im2col_cl_kernel(const Im2colClArgs a) {
   pdl_wait();
   pdl_launch_dependents();
-  const int c8n = a.C >> 3;
-  const int kk = a.kh * a.kw;
-  const int64_t total = int64_t(a.B) * a.OH * a.OW * kk * c8n;
+  // the kernel is pure address arithmetic + 16-byte copies: keep the arithmetic in 32 bits (the host checks the range)
+  const uint32_t c8n = uint32_t(a.C) >> 3;
+  const uint32_t kk = uint32_t(a.kh * a.kw);
+  const uint32_t per_row = kk * c8n;                                  // 16-byte vectors per patch-matrix row
+  const uint32_t M = uint32_t(a.B) * uint32_t(a.OH) * uint32_t(a.OW);
+  const uint32_t total = M * per_row;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int64_t e = int64_t(blockIdx.x) * NT + threadIdx.x; e < total; e += int64_t(gridDim.x) * NT) {
-    const int c8 = int(e % c8n);
-    int64_t t = e / c8n;
-    const int tap = int(t % kk);
-    const int64_t m = t / kk;
-    const int i = tap / a.kw, j = tap - i * a.kw;
-    const int ow = int(m % a.OW);
-    t = m / a.OW;
-    const int oh = int(t % a.OH);
-    const int64_t b = t / a.OH;
+  for (uint32_t e = blockIdx.x * NT + threadIdx.x; e < total; e += gridDim.x * NT) {
+    const uint32_t m = e / per_row;
+    const uint32_t r = e - m * per_row;
+    const uint32_t tap = r / c8n;
+    const uint32_t c8 = r - tap * c8n;
+    const int i = int(tap / uint32_t(a.kw)), j = int(tap) - i * a.kw;
+    const uint32_t t = m / uint32_t(a.OW);
+    const int ow = int(m - t * uint32_t(a.OW));
+    const uint32_t b = t / uint32_t(a.OH);
+    const int oh = int(t - b * uint32_t(a.OH));
     int h = oh * a.stride - a.pad + i, w = ow * a.stride - a.pad + j;
     bool ok = h >= 0 && w >= 0;
     if (a.dil > 1) {
@@ -65,8 +68,8 @@ __global__ void __launch_bounds__(NT) im2col_cl_kernel(const Im2colClArgs a) {
     }
     ok = ok && h < a.H && w < a.W;
     uint4 v = zero;
-    if (ok) v = *reinterpret_cast<const uint4*>(a.x + ((b * a.H + h) * a.W + w) * a.ld_x + (c8 << 3));
-    *reinterpret_cast<uint4*>(a.col + m * a.ld_col + int64_t(tap) * a.C + (c8 << 3)) = v;
+    if (ok) v = *reinterpret_cast<const uint4*>(a.x + (int64_t(b) * a.H * a.W + int64_t(h) * a.W + w) * a.ld_x + (c8 << 3));
+    *reinterpret_cast<uint4*>(a.col + int64_t(m) * a.ld_col + (r << 3)) = v;
   }
 }
 
@@ -80,6 +83,7 @@ static unsigned grid_for_total(int64_t total, int per_sm = 8) {
 int im2col_cl(const Im2colClArgs& a, cudaStream_t stream) {
   if ((a.C & 7) || (a.ld_x & 7) || (a.ld_col & 7)) return -1;
   const int64_t total = int64_t(a.B) * a.OH * a.OW * a.kh * a.kw * (a.C >> 3);
+  if (total >= (int64_t(1) << 31)) return -2;
   return int(launch_kernel(im2col_cl_kernel, dim3(grid_for_total(total, 16)), dim3(NT), 0, stream, a));
 }
 
@@ -221,23 +225,58 @@ int bn_finalize(float* sums, int64_t M, int C, float eps, float momentum, float*
                            running_mean, running_var, stats, from_running, update_running));
 }
 
+// Row walk shared by the element-wise kernels: thread -> fixed channel group (so per-channel constants are loaded once),
+// rows r0 + rl, r0 + rl + lanes, ... inside the block's row range.
+constexpr int EW_ITERS = 8;
+static unsigned ew_grid(int64_t M, int C) {
+  const int lanes = NT / (C >> 3) < 1 ? 1 : NT / (C >> 3);
+  const int64_t rpb = int64_t(lanes) * EW_ITERS;
+  return unsigned((M + rpb - 1) / rpb);
+}
+
 // z = relu?( (y - mean) * rstd * gamma + beta + residual? )
 __global__ void __launch_bounds__(NT) bn_apply_kernel(const BnArgs a) {
   pdl_wait();
   pdl_launch_dependents();
-  const int c8n = a.C >> 3;
-  const int64_t total = a.M * c8n;
-  for (int64_t e = int64_t(blockIdx.x) * NT + threadIdx.x; e < total; e += int64_t(gridDim.x) * NT) {
-    const int cg = int(e % c8n);
-    const int64_t m = e / c8n;
-    const int c0 = cg << 3;
+  const ColLayout l = col_layout(a.C);
+  if (l.rl >= l.lanes) return;
+  const int c0 = l.cg << 3;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float mean, rstd;
+    if (a.sums != nullptr) {
+      const float inv = 1.f / float(a.M);
+      mean = a.sums[c0 + i] * inv;
+      const float var = fmaxf(a.sums[a.C + c0 + i] * inv - mean * mean, 0.f);
+      rstd = rsqrtf(var + a.eps);
+      if (blockIdx.x == 0 && l.rl == 0) {       // one thread per channel group records what backward / eval need
+        a.stats_out[c0 + i] = mean;
+        a.stats_out[a.C + c0 + i] = rstd;
+        if (a.running_mean != nullptr) {
+          const float unb = a.M > 1 ? var * (float(a.M) / float(a.M - 1)) : var;
+          a.running_mean[c0 + i] = (1.f - a.momentum) * a.running_mean[c0 + i] + a.momentum * mean;
+          a.running_var[c0 + i] = (1.f - a.momentum) * a.running_var[c0 + i] + a.momentum * unb;
+        }
+      }
+    } else {
+      mean = a.stats[c0 + i];
+      rstd = a.stats[a.C + c0 + i];
+    }
+    sc[i] = rstd * a.gamma[c0 + i];
+    sh[i] = a.beta[c0 + i] - mean * sc[i];
+  }
+  const int64_t r0 = int64_t(blockIdx.x) * l.lanes * EW_ITERS;
+#pragma unroll 2
+  for (int it = 0; it < EW_ITERS; ++it) {
+    const int64_t m = r0 + l.rl + int64_t(it) * l.lanes;
+    if (m >= a.M) break;
     float y[8], r[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(a.y + m * a.ld + c0), y);
     if (a.residual != nullptr) unpack8(*reinterpret_cast<const uint4*>(a.residual + m * a.ld_res + c0), r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float mean = a.stats[c0 + i], rstd = a.stats[a.C + c0 + i];
-      float v = (y[i] - mean) * rstd * a.gamma[c0 + i] + a.beta[c0 + i];
+      float v = fmaf(y[i], sc[i], sh[i]);
       if (a.residual != nullptr) v += r[i];
       if (a.relu) v = fmaxf(v, 0.f);
       o[i] = v;
@@ -247,8 +286,8 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const BnArgs a) {
 }
 
 int bn_apply(const BnArgs& a, cudaStream_t stream) {
-  if ((a.C & 7) || (a.ld & 7) || (a.ld_z & 7) || (a.ld_res & 7)) return -1;
-  return int(launch_kernel(bn_apply_kernel, dim3(grid_for_total(a.M * (a.C >> 3), 16)), dim3(NT), 0, stream, a));
+  if ((a.C & 7) || a.C > 8 * NT || (a.ld & 7) || (a.ld_z & 7) || (a.ld_res & 7)) return -1;
+  return int(launch_kernel(bn_apply_kernel, dim3(ew_grid(a.M, a.C)), dim3(NT), 0, stream, a));
 }
 
 // g = (dz_a + dz_b?) * (relu ? z > 0 : 1);  dbeta[c] += sum g;  dgamma[c] += sum g * xhat
@@ -299,13 +338,24 @@ int bn_bwd_reduce(const BnArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const BnArgs a) {
   pdl_wait();
   pdl_launch_dependents();
-  const int c8n = a.C >> 3;
-  const int64_t total = a.M * c8n;
+  const ColLayout l = col_layout(a.C);
+  if (l.rl >= l.lanes) return;
+  const int c0 = l.cg << 3;
   const float inv_m = 1.f / float(a.M);
-  for (int64_t e = int64_t(blockIdx.x) * NT + threadIdx.x; e < total; e += int64_t(gridDim.x) * NT) {
-    const int cg = int(e % c8n);
-    const int64_t m = e / c8n;
-    const int c0 = cg << 3;
+  // dy = k1 * g - k2 * y + k3   with  k1 = gamma*rstd,  k2 = k1 * rstd * dgamma/M,  k3 = k2 * mean - k1 * dbeta/M
+  float k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mean = a.stats[c0 + i], rstd = a.stats[a.C + c0 + i];
+    k1[i] = a.gamma[c0 + i] * rstd;
+    k2[i] = k1[i] * rstd * a.dgamma[c0 + i] * inv_m;
+    k3[i] = k2[i] * mean - k1[i] * a.dbeta[c0 + i] * inv_m;
+  }
+  const int64_t r0 = int64_t(blockIdx.x) * l.lanes * EW_ITERS;
+#pragma unroll 2
+  for (int it = 0; it < EW_ITERS; ++it) {
+    const int64_t m = r0 + l.rl + int64_t(it) * l.lanes;
+    if (m >= a.M) break;
     float g[8], t[8], y[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(a.dz_a + m * a.ld_dz + c0), g);
     if (a.dz_b != nullptr) {
@@ -320,19 +370,15 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const BnArgs a) {
     }
     unpack8(*reinterpret_cast<const uint4*>(a.y + m * a.ld + c0), y);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float mean = a.stats[c0 + i], rstd = a.stats[a.C + c0 + i];
-      const float xhat = (y[i] - mean) * rstd;
-      o[i] = a.gamma[c0 + i] * rstd * (g[i] - a.dbeta[c0 + i] * inv_m - xhat * a.dgamma[c0 + i] * inv_m);
-    }
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(k1[i], g[i], fmaf(-k2[i], y[i], k3[i]));
     *reinterpret_cast<uint4*>(a.dy + m * a.ld_dy + c0) = pack8(o);
     if (a.g_out != nullptr) *reinterpret_cast<uint4*>(a.g_out + m * a.ld_dz + c0) = pack8(g);
   }
 }
 
 int bn_bwd_apply(const BnArgs& a, cudaStream_t stream) {
-  if ((a.C & 7) || (a.ld & 7) || (a.ld_z & 7) || (a.ld_dz & 7) || (a.ld_dy & 7)) return -1;
-  return int(launch_kernel(bn_bwd_apply_kernel, dim3(grid_for_total(a.M * (a.C >> 3), 16)), dim3(NT), 0, stream, a));
+  if ((a.C & 7) || a.C > 8 * NT || (a.ld & 7) || (a.ld_z & 7) || (a.ld_dz & 7) || (a.ld_dy & 7)) return -1;
+  return int(launch_kernel(bn_bwd_apply_kernel, dim3(ew_grid(a.M, a.C)), dim3(NT), 0, stream, a));
 }
 
 // ------------------------------------------------------------------------------------------------ pooling

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -242,6 +243,7 @@ class FusedResNet:
             if g["k"] > 1:
                 self.Wflip[id(u)] = torch.zeros(g["Cin"], g["k"] * g["k"] * g["Cout"], dtype=torch.bfloat16, device=device)
         self.window = None
+        self.bn_in_epilogue = os.environ.get("SPARKTORCH_BN_EPILOGUE", "1") == "1"
         self.train = self._alloc(batch, backward=True)
         self.val = self._alloc(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
@@ -252,12 +254,16 @@ class FusedResNet:
         dev, bf = self.device, torch.bfloat16
         z = lambda r, c_: torch.zeros(r, c_, dtype=bf, device=dev)          # noqa: E731
         buf = {"rows": rows, "acts": [torch.zeros(rows, _pad(self.d0), dtype=bf, device=dev)[:, : self.d0]], "u": {}}
+        # batch-norm accumulators of all units in one slab: cleared by a single memset at the top of forward
+        buf["sums_all"] = torch.zeros(sum(2 * u.g["Cout"] for u in self.units), dtype=torch.float32, device=dev)
+        so = 0
         for i, u in enumerate(self.units):
             g = u.g
             M = rows * g["OH"] * g["OW"]
             ub = {"M": M, "Y": z(M, g["Cout"]), "Z": z(M, g["Cout"]),
-                  "sums": torch.zeros(2 * g["Cout"], dtype=torch.float32, device=dev),
+                  "sums": buf["sums_all"][so: so + 2 * g["Cout"]],
                   "stats": torch.zeros(2 * g["Cout"], dtype=torch.float32, device=dev)}
+            so += 2 * g["Cout"]
             if not g["direct"]:
                 ub["col"] = z(M, _pad(g["K"]))[:, : g["K"]]
             if backward:
@@ -314,21 +320,31 @@ class FusedResNet:
             C.im2col_cl(x, rows, g["H"], g["W"], g["Cin"], g["k"], g["k"], g["s"], g["p"], 1, g["OH"], g["OW"], ub["col"])
             self.n_launch += 1
             a = ub["col"]
-        self._gemm(a, False, self.Wb[id(u.conv)], False, M, g["Cout"], g["K"], out_bf16=ub["Y"])
         bn = u.bn
-        batch_stats = train or not getattr(self, "eval_running", False)
-        if batch_stats:
-            C.bn_stats(ub["Y"], M, g["Cout"], ub["sums"])
-            self.n_launch += 1
-        C.bn_finalize(ub["sums"], M, g["Cout"], bn.eps, bn.momentum, bn.running_mean, bn.running_var, ub["stats"],
-                      from_running=not batch_stats, update_running=train)
         gamma, beta = self.vec[id(bn.weight)][0], self.vec[id(bn.bias)][0]
-        C.bn_apply(ub["Y"], M, g["Cout"], ub["stats"], gamma, beta, ub["Z"], relu=u.relu, residual=residual)
-        self.n_launch += 2
+        Cout = g["Cout"]
+        if self.bn_in_epilogue:
+            # batch statistics are column sums of the GEMM output: reduced in its epilogue, finalised inside bn_apply
+            self._gemm(a, False, self.Wb[id(u.conv)], False, M, Cout, g["K"], out_bf16=ub["Y"], colsum=ub["sums"][:Cout],
+                       colsumsq=ub["sums"][Cout:])
+            C.bn_apply(ub["Y"], M, Cout, ub["stats"], gamma, beta, ub["Z"], relu=u.relu, residual=residual, sums=ub["sums"],
+                       eps=bn.eps, momentum=bn.momentum, running_mean=bn.running_mean if train else None,
+                       running_var=bn.running_var if train else None)
+            self.n_launch += 1
+            return ub["Z"]
+        self._gemm(a, False, self.Wb[id(u.conv)], False, M, Cout, g["K"], out_bf16=ub["Y"])
+        C.bn_stats(ub["Y"], M, Cout, ub["sums"])
+        C.bn_finalize(ub["sums"], M, Cout, bn.eps, bn.momentum, bn.running_mean, bn.running_var, ub["stats"],
+                      from_running=False, update_running=train)
+        C.bn_apply(ub["Y"], M, Cout, ub["stats"], gamma, beta, ub["Z"], relu=u.relu, residual=residual)
+        self.n_launch += 3
         return ub["Z"]
 
     def forward(self, buf, slot=None, train: bool = False, windowed: bool = False) -> None:
         C, rows, low = self.C, buf["rows"], self.low
+        if self.bn_in_epilogue:
+            buf["sums_all"].zero_()
+            self.n_launch += 1
         zs = self._unit_fwd(buf, low.stem, None, train, stem_src=buf["acts"][0])
         sg = low.stem.g
         pk, ps, pp = low.pool

@@ -68,8 +68,10 @@ def test_forward_backward_match_autograd(depth):
         model = ResNet(ncls, image)
     else:
         model = _small_resnet(ncls, image)
-    # 50 layers of bf16 activations between fp32 batch-norms drift visibly from an fp32 run; 7 layers do not
-    tol_logits, tol_grad, tol_fc = (0.995, 0.97, 0.995) if depth == "shallow" else (0.93, 0.70, 0.95)
+    # Random-init batch-norm nets amplify rounding noise layer by layer (tiny batch statistics), so the yardstick is
+    # what torch's own bf16 autocast run loses against fp32 on the same net: we must not be worse than that by more
+    # than a margin, parameter by parameter.
+    tol_logits, tol_fc = (0.995, 0.995) if depth == "shallow" else (0.93, 0.95)
     ref = copy.deepcopy(model).to(dev).float().train()
     g = torch.Generator().manual_seed(1)
     x = torch.randn(batch, 3 * image * image, generator=g).to(torch.bfloat16)
@@ -93,11 +95,21 @@ def test_forward_backward_match_autograd(depth):
     logits = plan.train["logits"].float()
     assert _cos(logits, out.detach()) > tol_logits, _cos(logits, out.detach())
     got = dict(model.named_parameters())
-    worst = 1.0
+    amp = copy.deepcopy(ref)
+    amp.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        nn.functional.cross_entropy(amp(x.to(dev).float()).float(), y.to(dev)).backward()
+    amp_grads = {n: p.grad for n, p in amp.named_parameters()}
+    worst, bad = 1.0, []
     for name, p in ref.named_parameters():
         c = _cos(got[name].grad, p.grad)
+        tol_grad = min(0.97, _cos(amp_grads[name], p.grad) - 0.10)
+        ratio = float(got[name].grad.norm() / (p.grad.norm() + 1e-30))
+        print(f"  {name:32s} cos {c:.4f} (autocast {_cos(amp_grads[name], p.grad):.4f})  |ours|/|ref| {ratio:.3f}")
         worst = min(worst, c)
-        assert c > tol_grad, (name, c)
+        if c <= tol_grad:
+            bad.append((name, round(c, 4)))
+    assert not bad, bad
     # running statistics follow nn.BatchNorm2d
     for (n1, b1), (n2, b2) in zip(model.named_buffers(), ref.named_buffers()):
         if n1.endswith("running_mean") or n1.endswith("running_var"):
