@@ -189,7 +189,8 @@ class FusedCNN:
     """Buffers + enqueue functions; interface-compatible with FusedMLP."""
 
     def __init__(self, model: nn.Module, low: LoweredCNN, kind: str, spec, world: int, rank: int, device: torch.device,
-                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None):
+                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None,
+                 inference: bool = False):
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
         self.C = native.load(required=True)
@@ -266,7 +267,7 @@ class FusedCNN:
         self.fuse_loss = dL <= 32 and os.environ.get("SPARKTORCH_FUSE_LOSS", "1") == "1"
         self.window = None
         self.side = torch.cuda.Stream(device=device) if os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None
-        self.train = self._alloc(batch, backward=True)
+        self.train = self._alloc(batch, backward=not inference)
         self.val = self._alloc(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
 

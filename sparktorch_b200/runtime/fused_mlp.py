@@ -596,7 +596,7 @@ def try_fused_predictor(model: nn.Module, device: torch.device, precision: str =
         return None
     lowered = lower_mlp(model)
     if lowered is None:
-        return None
+        return _ConvPredictor(model, device) if any(isinstance(m, nn.Conv2d) for m in model.modules()) else None
     C = native.load(required=True)
     d = [lowered.layers[0].module.in_features] + [ls.module.out_features for ls in lowered.layers]
     Wb, bias = [], []
@@ -625,3 +625,68 @@ def try_fused_predictor(model: nn.Module, device: torch.device, precision: str =
         return a
 
     return run
+
+
+class _ConvPredictor:
+    """Inference through the fused CNN / ResNet plans (forward kernels only).  The input width is only known at the
+    first batch, so lowering happens then; nets that do not lower keep running through ``model(x)``."""
+
+    def __init__(self, model: nn.Module, device: torch.device):
+        self.model, self.device = model, device
+        self.plan = None
+        self.failed = False
+        self.engine = None
+
+    def _build(self, in_features: int) -> None:
+        from sparktorch_b200.runtime.fused_cnn import FusedCNN, lower_cnn
+        from sparktorch_b200.runtime.fused_resnet import FusedResNet, lower_resnet
+
+        spec = parse_optimizer(torch.optim.SGD, {"lr": 0.0})
+        low = lower_cnn(self.model, in_features)
+        if low is not None:
+            per_row = sum(g_["OH"] * g_["OW"] * (g_["K"] + g_["Cout"]) for g_ in _cnn_geo(low)) * 2
+            self.chunk = int(max(64, min(8192, (1 << 30) // max(1, per_row))))
+            kind = "ce" if low.linears[-1].module.out_features > 1 else "mse"
+            self.plan = FusedCNN(self.model, low, kind, spec, 1, 0, self.device, self.chunk, 0, 0, 1, inference=True)
+            self.engine = "fused_cnn"
+        else:
+            low = lower_resnet(self.model, in_features)
+            if low is None:
+                self.failed = True
+                return
+            self.chunk = 64
+            self.plan = FusedResNet(self.model, low, "ce", spec, 1, 0, self.device, self.chunk, 0, 0, 1, inference=True)
+            self.engine = "fused_resnet"
+        self.low = low
+        self.plan.fu.updater.publish()
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if self.plan is None and not self.failed:
+            try:
+                self._build(int(x.shape[1]))
+            except Exception:
+                self.failed = True
+        if self.failed:
+            return self.model(x)
+        buf, outs = self.plan.train, []
+        for s in range(0, x.shape[0], self.chunk):
+            xb = x[s: s + self.chunk]
+            buf["acts"][0][: xb.shape[0]].copy_(xb)
+            self.plan.forward(buf, slot=None, train=False)
+            outs.append(buf["logits"][: xb.shape[0]].clone())
+        out = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        return torch.log_softmax(out, dim=1) if getattr(self.low, "final_log_softmax", False) else out
+
+
+def _cnn_geo(low):
+    c, h, w = low.in_shape
+    out = []
+    for cs in low.convs:
+        m = cs.module
+        k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+        st = m.stride if isinstance(m.stride, int) else m.stride[0]
+        p = m.padding if isinstance(m.padding, int) else m.padding[0]
+        oh, ow = (h + 2 * p - k) // st + 1, (w + 2 * p - k) // st + 1
+        out.append(dict(OH=oh, OW=ow, K=c * k * k, Cout=m.out_channels))
+        c, h, w = m.out_channels, oh // (cs.pool or 1), ow // (cs.pool or 1)
+    return out

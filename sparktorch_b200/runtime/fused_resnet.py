@@ -153,10 +153,12 @@ class FusedResNet:
     fuse_loss = False          # the 1000-way loss is its own kernel, batches are gathered (no in-GEMM windows)
 
     def __init__(self, model: nn.Module, low: LoweredResNet, kind: str, spec, world: int, rank: int, device: torch.device,
-                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None):
+                 batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None,
+                 inference: bool = False):
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
         assert kind == "ce" and backend_factory is None
+        self.eval_running = inference        # inference: BatchNorm uses the running statistics (module.eval())
         self.C = native.load(required=True)
         self.device, self.world, self.rank = device, world, rank
         self.kind, self.low, self.lowered = kind, low, low
@@ -244,7 +246,7 @@ class FusedResNet:
                 self.Wflip[id(u)] = torch.zeros(g["Cin"], g["k"] * g["k"] * g["Cout"], dtype=torch.bfloat16, device=device)
         self.window = None
         self.bn_in_epilogue = os.environ.get("SPARKTORCH_BN_EPILOGUE", "1") == "1"
-        self.train = self._alloc(batch, backward=True)
+        self.train = self._alloc(batch, backward=not inference)
         self.val = self._alloc(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
         self._bn_saved = None
@@ -323,6 +325,13 @@ class FusedResNet:
         bn = u.bn
         gamma, beta = self.vec[id(bn.weight)][0], self.vec[id(bn.bias)][0]
         Cout = g["Cout"]
+        if self.eval_running and not train:
+            self._gemm(a, False, self.Wb[id(u.conv)], False, M, Cout, g["K"], out_bf16=ub["Y"])
+            C.bn_finalize(ub["sums"], M, Cout, bn.eps, bn.momentum, bn.running_mean, bn.running_var, ub["stats"],
+                          from_running=True, update_running=False)
+            C.bn_apply(ub["Y"], M, Cout, ub["stats"], gamma, beta, ub["Z"], relu=u.relu, residual=residual)
+            self.n_launch += 2
+            return ub["Z"]
         if self.bn_in_epilogue:
             # batch statistics are column sums of the GEMM output: reduced in its epilogue, finalised inside bn_apply
             self._gemm(a, False, self.Wb[id(u.conv)], False, M, Cout, g["K"], out_bf16=ub["Y"], colsum=ub["sums"][:Cout],

@@ -137,8 +137,9 @@ def main():
 
     for lock in (True, False):
         cfg = TrainConfig(iters=60, mini_batch=128, device="cuda", seed=9)
-        hw = train_partition_hogwild(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3},
-                                     X, Y, cfg, dev, acquire_lock=lock, window_len=world)
+        # W asynchronous workers apply W optimizer steps per "iteration": keep the effective step size constant
+        hw = train_partition_hogwild(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam,
+                                     {"lr": 2e-3 / world}, X, Y, cfg, dev, acquire_lock=lock, window_len=world)
         hh = hw.history
         assert np.isfinite(hh["train_loss"]).all() and np.mean(hh["train_loss"][-8:]) < 0.8 * np.mean(hh["train_loss"][:3]), hh["train_loss"][::10]
         if rank == 0:
@@ -149,8 +150,8 @@ def main():
     from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
 
     cfg = TrainConfig(iters=200, mini_batch=256, device="cuda", seed=9, sampling="sweep")
-    hf = train_partition_hogwild_fused(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y,
-                                       cfg, dev, window_len=world)
+    hf = train_partition_hogwild_fused(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam,
+                                       {"lr": 2e-3 / world}, X, Y, cfg, dev, window_len=world)
     assert hf is not None and hf.history["iters_run"] == 200
     tl = hf.history["train_loss"]
     assert np.isfinite(tl).all() and np.mean(tl[-10:]) < 0.7 * np.mean(tl[:3]), tl[::20]
