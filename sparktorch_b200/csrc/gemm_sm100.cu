@@ -37,7 +37,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (STAGE_BYTES * 8 <= 200 * 1024) ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int BAR_BYTES = 2048;   // mbarriers + tmem slot (first 512 B), bias tile (up to 256 floats)
+  static constexpr int BAR_BYTES = 4096;   // mbarriers + tmem slot (first 512 B), bias tile (256 floats), per-CTA column statistics (2 x 256 floats)
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
@@ -47,7 +47,7 @@ struct GemmSmem {
 template <int CHUNK>
 ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], const uint4 (&mk)[4], bool have_mask,
                               const __nv_bfloat16* mrow, bool have_bias, const float* s_bias, int c0, int row, bool row_ok,
-                              int col0, int N, int lane, int lbl_off) {
+                              int col0, int N, int lane, int lbl_off, float* s_sum = nullptr, float* s_sq = nullptr) {
   const bool vec_ok = (col0 + CHUNK <= N);   // leading dims are multiples of 8 elements, col0 multiple of 16
   float loss_part = 0.f, colsum_part = 0.f;     // what this thread added to the loss slot / its bias-gradient column
   float acc[32];
@@ -192,7 +192,10 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
       }
     }
     colsum_part = v[0];
-    if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsum + col0 + lane, colsum_part);
+    if (lane < CHUNK && col0 + lane < N) {
+      if (s_sum != nullptr) atomicAdd(s_sum + c0 + lane, colsum_part);     // persistent CTA: flushed once per column tile
+      else red_add_f32(ep.colsum + col0 + lane, colsum_part);
+    }
   }
   // ---- column sums of squares (with colsum: the batch-norm statistics of a convolution output, no extra pass)
   if (ep.colsumsq != nullptr) {
@@ -209,7 +212,10 @@ ST_DEVINL void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], c
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
       }
     }
-    if (lane < CHUNK && col0 + lane < N) red_add_f32(ep.colsumsq + col0 + lane, v[0]);
+    if (lane < CHUNK && col0 + lane < N) {
+      if (s_sq != nullptr) atomicAdd(s_sq + c0 + lane, v[0]);
+      else red_add_f32(ep.colsumsq + col0 + lane, v[0]);
+    }
   }
   // ---- GEMM -> all-gather push (one warp-uniform branch; nothing of this is issued on the normal path):
   //      repeat every write that went into the LOCAL gradient arena into my receive slot on each peer.
@@ -608,13 +614,33 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     constexpr int CHUNK = 32;
     const bool have_bias = ep.bias != nullptr;
     const bool have_mask = ep.mask_src != nullptr;
+    // Batch-norm statistics (column sums + sums of squares): thousands of row tiles would hammer the same few cache
+    // lines with global atomics, so a CTA accumulates in shared memory and flushes when it moves to another column tile.
+    const bool stat_mode = ep.colsum != nullptr && ep.colsumsq != nullptr && ep.push_world <= 1;
+    float* s_sum = stat_mode ? s_bias + 256 : nullptr;
+    float* s_sq = stat_mode ? s_bias + 512 : nullptr;
+    int stat_n0 = -1;
+    auto flush_stats = [&]() {                                  // callers bracket this with bar.sync 1
+      for (int c = et; c < BLOCK_N; c += 128) {
+        if (stat_n0 >= 0 && stat_n0 + c < N) {
+          red_add_f32(ep.colsum + stat_n0 + c, s_sum[c]);
+          red_add_f32(ep.colsumsq + stat_n0 + c, s_sq[c]);
+        }
+        s_sum[c] = 0.f;
+        s_sq[c] = 0.f;
+      }
+    };
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
       const uint32_t as = t & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's s_bias readers are done
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's s_bias readers / statistic adders are done
+      if (stat_mode && n0 != stat_n0) {
+        flush_stats();
+        stat_n0 = n0;
+      }
       if (have_bias)
         for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (n0 + c < N) ? ep.bias[n0 + c] : 0.f;
       const __nv_bfloat16* mrow = have_mask ? ep.mask_src + size_t(row_ok ? row : 0) * ep.ld_mask : nullptr;
@@ -649,9 +675,13 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
         if (!live) break;
-        epilogue_chunk<CHUNK>(ep, r, mk, have_mask, mrow, have_bias, s_bias, c0, row, row_ok, col0, N, lane, 0);
+        epilogue_chunk<CHUNK>(ep, r, mk, have_mask, mrow, have_bias, s_bias, c0, row, row_ok, col0, N, lane, 0, s_sum, s_sq);
         if (col0 + CHUNK >= N) break;
       }
+    }
+    if (stat_mode) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      flush_stats();
     }
   }
 

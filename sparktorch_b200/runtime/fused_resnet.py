@@ -245,7 +245,7 @@ class FusedResNet:
             if g["k"] > 1:
                 self.Wflip[id(u)] = torch.zeros(g["Cin"], g["k"] * g["k"] * g["Cout"], dtype=torch.bfloat16, device=device)
         self.window = None
-        self.bn_in_epilogue = os.environ.get("SPARKTORCH_BN_EPILOGUE", "1") == "1"
+        self.bn_in_epilogue = os.environ.get("SPARKTORCH_BN_EPILOGUE", "0") == "1"
         self.train = self._alloc(batch, backward=not inference)
         self.val = self._alloc(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0

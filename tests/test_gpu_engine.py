@@ -296,7 +296,8 @@ def test_hogwild_fused_worker_matches_sync_fused_on_one_gpu():
     for k in ref.state_dict:
         # fp32 atomics reorder between the two runs; Adam turns a sign flip of a ~0 gradient into +-lr, so compare in bulk
         d = (hw.state_dict[k] - ref.state_dict[k]).abs()
-        assert float((d <= 1e-4 + 1e-2 * ref.state_dict[k].abs()).float().mean()) > 0.99 and float(d.max()) < 5e-3, (k, float(d.max()))
+        n_bad = int((d > 1e-4 + 1e-2 * ref.state_dict[k].abs()).sum())
+        assert n_bad <= max(2, d.numel() // 100) and float(d.max()) < 5e-3, (k, n_bad, float(d.max()))
 
 
 def test_fused_cnn_predictor_matches_eager():
