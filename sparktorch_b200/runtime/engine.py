@@ -326,47 +326,60 @@ def train_partition(
     stopped_at = None
     t_loop = time.time()
 
-    for i in range(start_iter, cfg.iters):
-        _maybe_inject_fault(cfg, rank, i)
-        window.before_step(i)
-        if stream_host:
-            # sequential sweep over the (already shuffled) pinned partition
-            lo = (i * cfg.mini_batch) % (n - cfg.mini_batch + 1)
-            xb = x_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
-            yb = xb if y_all is x_all else y_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
-            h2d_bytes = xb.numel() * xb.element_size() + (0 if yb is xb else yb.numel() * yb.element_size())
-        elif sampler is not None:
-            idx = sampler.next()
-            xb, yb = x_all[idx], (y_all[idx] if y_all is not x_all else None)
-            if yb is None:
-                yb = xb
-        else:
-            xb, yb = x_all, y_all
-        with tracer.phase("forward_backward"):
-            loss = step.run(xb, yb)
-        val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
-        # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
-        arena.tail[0] = val_loss if val_loss is not None else loss
-        loss_buf[i] = loss
-        with tracer.phase("exchange_update"):
-            res = comm.reduce_and_update(need_loss)
-        if host_loss is not None:     # per-step device→host read of the step result
-            host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
-            d2h_bytes = 4
-        window.after_step(i)
-        if cfg.verbose:
-            print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {res.loss} "
-                  f"Partition Training Loss: {float(loss)}, "
-                  f"Partition Validation Loss: {None if val_loss is None else float(val_loss)}")
-        if res.stop:
-            stopped_at = i
-            break
-        if cfg.checkpoint_dir and cfg.checkpoint_every > 0 and (i + 1) % cfg.checkpoint_every == 0:
-            comm.finish()
-            ckpt.save(cfg.checkpoint_dir, rank, {
-                "numel": arena.numel, "flat_p": arena.flat_p.detach().cpu(), "comm": comm.export_state(),
-                "iters_done": i + 1, "losses": loss_buf[: i + 1].detach().cpu().tolist()})
-    comm.finish()
+    # peers of a dead rank would spin in the K-AR flag barrier forever: turn that into a loud task failure
+    progress = [start_iter]
+    stall_guard = None
+    if world > 1 and getattr(comm, "fused", False):
+        from sparktorch_b200.utils.watchdog import ProgressWatchdog
+
+        stall_guard = ProgressWatchdog(lambda: progress[0], label=f"rank {rank} eager loop")
+        stall_guard.__enter__()
+    try:
+        for i in range(start_iter, cfg.iters):
+            progress[0] = i
+            _maybe_inject_fault(cfg, rank, i)
+            window.before_step(i)
+            if stream_host:
+                # sequential sweep over the (already shuffled) pinned partition
+                lo = (i * cfg.mini_batch) % (n - cfg.mini_batch + 1)
+                xb = x_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
+                yb = xb if y_all is x_all else y_all[lo:lo + cfg.mini_batch].to(device, non_blocking=True)
+                h2d_bytes = xb.numel() * xb.element_size() + (0 if yb is xb else yb.numel() * yb.element_size())
+            elif sampler is not None:
+                idx = sampler.next()
+                xb, yb = x_all[idx], (y_all[idx] if y_all is not x_all else None)
+                if yb is None:
+                    yb = xb
+            else:
+                xb, yb = x_all, y_all
+            with tracer.phase("forward_backward"):
+                loss = step.run(xb, yb)
+            val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
+            # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
+            arena.tail[0] = val_loss if val_loss is not None else loss
+            loss_buf[i] = loss
+            with tracer.phase("exchange_update"):
+                res = comm.reduce_and_update(need_loss)
+            if host_loss is not None:     # per-step device→host read of the step result
+                host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+                d2h_bytes = 4
+            window.after_step(i)
+            if cfg.verbose:
+                print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {res.loss} "
+                      f"Partition Training Loss: {float(loss)}, "
+                      f"Partition Validation Loss: {None if val_loss is None else float(val_loss)}")
+            if res.stop:
+                stopped_at = i
+                break
+            if cfg.checkpoint_dir and cfg.checkpoint_every > 0 and (i + 1) % cfg.checkpoint_every == 0:
+                comm.finish()
+                ckpt.save(cfg.checkpoint_dir, rank, {
+                    "numel": arena.numel, "flat_p": arena.flat_p.detach().cpu(), "comm": comm.export_state(),
+                    "iters_done": i + 1, "losses": loss_buf[: i + 1].detach().cpu().tolist()})
+        comm.finish()
+    finally:
+        if stall_guard is not None:
+            stall_guard.__exit__()
     if tracer.enabled:
         tracer.dump_chrome_trace(trace_path(rank), rank)
     n_done = cfg.iters if stopped_at is None else stopped_at + 1

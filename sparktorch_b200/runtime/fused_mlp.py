@@ -545,28 +545,36 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
             w0, wk = cfg.time_window
             segments = [(0, w0), (w0, w0 + wk), (w0 + wk, cfg.iters)]
         printed = 0
-        for seg_i, (lo, hi) in enumerate(segments):
-            if hi <= lo:
-                continue
-            timed = cfg.time_window is not None and seg_i == 1
-            if timed:
-                window.before_step(lo)
-            if cfg.verbose:
-                for i in range(lo, hi):
-                    got = runner.run(i, 1, mail_ptr, 1)
-                    stream.synchronize()
-                    done += got
-                    print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {plan.fu.last_loss()}")
-                    printed += 1
-                    if plan.fu.stopped():
-                        break
-            else:
-                done += runner.run(lo, hi - lo, mail_ptr, check)
-            if timed:
-                window.after_step(hi - 1)
-            if plan.fu.stopped():
-                break
-        stream.synchronize()
+        from sparktorch_b200.utils.watchdog import ProgressWatchdog
+
+        mailbox = plan.fu.mailbox
+        wd = ProgressWatchdog(lambda: int(mailbox[1]), label=f"rank {rank} fused loop")
+        wd.__enter__()
+        try:
+            for seg_i, (lo, hi) in enumerate(segments):
+                if hi <= lo:
+                    continue
+                timed = cfg.time_window is not None and seg_i == 1
+                if timed:
+                    window.before_step(lo)
+                if cfg.verbose:
+                    for i in range(lo, hi):
+                        got = runner.run(i, 1, mail_ptr, 1)
+                        stream.synchronize()
+                        done += got
+                        print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {plan.fu.last_loss()}")
+                        printed += 1
+                        if plan.fu.stopped():
+                            break
+                else:
+                    done += runner.run(lo, hi - lo, mail_ptr, check)
+                if timed:
+                    window.after_step(hi - 1)
+                if plan.fu.stopped():
+                    break
+            stream.synchronize()
+        finally:
+            wd.__exit__()
     torch.cuda.synchronize(device)
     t_end = time.time()
     n_done = plan.fu.iters_done()

@@ -74,3 +74,23 @@ def test_tracing_and_metrics(tmp_path, monkeypatch):
     text = metrics.to_prometheus(res.history)
     assert "sparktorch_iterations_total" in text and metrics.throughput(res.history) > 0
     assert len(metrics.to_jsonl(res.history).splitlines()) == 6
+
+
+def test_progress_watchdog_fires_on_stall_and_stays_quiet_on_progress():
+    import time
+
+    from sparktorch_b200.utils.watchdog import ProgressWatchdog
+
+    fired = []
+    counter = [0]
+    with ProgressWatchdog(lambda: counter[0], timeout_s=0.3, label="t", on_stall=fired.append, poll_s=0.05) as wd:
+        for _ in range(12):              # steady progress for 0.6 s: must not fire
+            counter[0] += 1
+            time.sleep(0.05)
+        assert not fired and not wd.fired
+        time.sleep(0.6)                  # progress stops
+    assert len(fired) == 1 and "no progress" in fired[0] and "iteration 12" in fired[0]
+    quiet = []
+    with ProgressWatchdog(lambda: 0, timeout_s=0, on_stall=quiet.append):    # disabled
+        time.sleep(0.1)
+    assert not quiet
