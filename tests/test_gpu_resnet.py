@@ -46,15 +46,6 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-def test_lowering_matches_structure_cpu_free():
-    from sparktorch_b200.runtime.fused_resnet import lower_resnet
-
-    m = _small_resnet()
-    low = lower_resnet(m, 3 * 64 * 64)
-    assert low is not None and len(low.blocks) == 16 and low.pool == (3, 2, 1)
-    assert lower_resnet(m, 3 * 32 * 32) is None
-
-
 @pytest.mark.parametrize("depth", ["shallow", "resnet50"])
 def test_forward_backward_match_autograd(depth):
     batch = 16 if depth == "shallow" else 8
