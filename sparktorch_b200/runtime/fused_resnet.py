@@ -154,12 +154,13 @@ class FusedResNet:
 
     def __init__(self, model: nn.Module, low: LoweredResNet, kind: str, spec, world: int, rank: int, device: torch.device,
                  batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None,
-                 inference: bool = False):
-        from sparktorch_b200.parallel.p2p import FusedUpdate
-
-        assert kind == "ce" and backend_factory is None
+                 inference: bool = False, ops=None, act_dtype: torch.dtype = torch.bfloat16):
+        """``backend_factory(numel, wbf16_elems)`` / ``ops`` / ``act_dtype`` exist for the CPU emulation of the plan
+        (runtime/emulation.py + ops/reference.py); production uses FusedUpdate, the native extension and bf16."""
+        assert kind == "ce"
         self.eval_running = inference        # inference: BatchNorm uses the running statistics (module.eval())
-        self.C = native.load(required=True)
+        self.act_dtype = act_dtype
+        self.C = ops if ops is not None else native.load(required=True)
         self.device, self.world, self.rank = device, world, rank
         self.kind, self.low, self.lowered = kind, low, low
         self.B, self.nv = batch, val_rows
@@ -201,7 +202,12 @@ class FusedResNet:
         for m, rows, cols in [(u.conv, u.g["Cout"], u.g["K"]) for u in self.units] + [(low.fc, self.ncls, c)]:
             w_off[id(m)] = (off, rows, cols)
             off += _pad(rows * _pad(cols), 64)
-        self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
+        if backend_factory is not None:
+            self.fu = backend_factory(numel, off)
+        else:
+            from sparktorch_b200.parallel.p2p import FusedUpdate
+
+            self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off)
         for bn in [u.bn for u in self.units]:                       # buffers live on the device, kernels update them
             bn.running_mean.data = bn.running_mean.data.to(device=device, dtype=torch.float32).contiguous()
             bn.running_var.data = bn.running_var.data.to(device=device, dtype=torch.float32).contiguous()
@@ -243,7 +249,7 @@ class FusedResNet:
         for u in self.units[1:]:
             g = u.g
             if g["k"] > 1:
-                self.Wflip[id(u)] = torch.zeros(g["Cin"], g["k"] * g["k"] * g["Cout"], dtype=torch.bfloat16, device=device)
+                self.Wflip[id(u)] = torch.zeros(g["Cin"], g["k"] * g["k"] * g["Cout"], dtype=self.fu.wbf16.dtype, device=device)
         self.window = None
         self.bn_in_epilogue = os.environ.get("SPARKTORCH_BN_EPILOGUE", "0") == "1"
         self.train = self._alloc(batch, backward=not inference)
@@ -253,7 +259,7 @@ class FusedResNet:
 
     # ------------------------------------------------------------------------------------------------
     def _alloc(self, rows: int, backward: bool):
-        dev, bf = self.device, torch.bfloat16
+        dev, bf = self.device, self.act_dtype
         z = lambda r, c_: torch.zeros(r, c_, dtype=bf, device=dev)          # noqa: E731
         buf = {"rows": rows, "acts": [torch.zeros(rows, _pad(self.d0), dtype=bf, device=dev)[:, : self.d0]], "u": {}}
         # batch-norm accumulators of all units in one slab: cleared by a single memset at the top of forward
