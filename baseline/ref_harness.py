@@ -40,11 +40,10 @@ def install_backend_patch() -> None:
     dist.init_process_group = patched
 
 
-class TimedAdam(torch.optim.Adam):
-    """Adam whose zero_grad() marks iteration boundaries."""
+class _IterationTimer:
+    """Mixin: zero_grad() marks iteration boundaries (the reference calls it once per iteration)."""
 
-    def __init__(self, params, warmup=3, steps=10, out_dir="/tmp", **kw):
-        super().__init__(params, **kw)
+    def _init_timer(self, warmup, steps, out_dir):
         self._w, self._k, self._n, self._out = int(warmup), int(steps), 0, out_dir
         self._e0 = self._e1 = None
         self._t0 = None
@@ -85,3 +84,15 @@ class TimedAdam(torch.optim.Adam):
                 json.dump({"device_ms": ms, "wall_ms": wall, "steps": self._k, "host_t0": self._host_t0, "host_t1": time.time()}, fh)
             self._fence()
         return super().zero_grad(set_to_none)
+
+
+class TimedAdam(_IterationTimer, torch.optim.Adam):
+    def __init__(self, params, warmup=3, steps=10, out_dir="/tmp", **kw):
+        torch.optim.Adam.__init__(self, params, **kw)
+        self._init_timer(warmup, steps, out_dir)
+
+
+class TimedSGD(_IterationTimer, torch.optim.SGD):
+    def __init__(self, params, warmup=3, steps=10, out_dir="/tmp", **kw):
+        torch.optim.SGD.__init__(self, params, **kw)
+        self._init_timer(warmup, steps, out_dir)
