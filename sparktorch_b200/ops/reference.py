@@ -23,15 +23,30 @@ def _f(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- GEMM
+def _window_offset(win_state, window_rows, n_windows) -> int:
+    it = int(win_state[4]) + (int(win_state[5]) << 32)            # StepState.iter (int64 at int32 words 4..5)
+    return (it % max(1, n_windows)) * window_rows
+
+
 def gemm_bf16(A, a_mn, B, b_mn, M, N, K, alpha: float = 1.0, bias=None, relu: bool = False, mask_src=None, out_bf16=None,
               out_t_bf16=None, out_f32=None, out_t_f32=None, atomic_f32: bool = False, colsum=None, block_n: int = 0,
-              split_k: int = 1, colsumsq=None, **unsupported):
-    """D[M, N] = A · Bᵀ with the epilogue options the plans use (A stored [M,K], or [K,M] when ``a_mn``; same for B)."""
+              split_k: int = 1, loss_kind: int = 0, labels=None, target=None, loss_slot=None, loss_scale: float = 1.0,
+              win_state=None, window_rows: int = 0, n_windows: int = 0, win_flags: int = 0, colsumsq=None, **unsupported):
+    """D[M, N] = A · Bᵀ with the epilogue options the plans use (A stored [M,K], or [K,M] when ``a_mn``; same for B).
+
+    ``win_flags``: 1 - A is the resident partition, the batch is the window of the current iteration; 2 - same for the
+    reduction rows of an MN-major B; 4 - labels / targets are taken from the same window.
+    ``loss_kind`` 1 (softmax-CE, mean over rows) / 2 (MSE, mean over M*N): the accumulator becomes dLoss/dOutput, so
+    ``out_bf16`` / ``colsum`` emit dZ / db while ``out_f32`` keeps the raw output."""
     for k, v in unsupported.items():
         if v not in (None, 0, False, 0.0, 1.0):
             raise NotImplementedError(f"reference gemm_bf16: option {k} is not emulated")
-    Am = _f(A[:K, :M]).t() if a_mn else _f(A[:M, :K])
-    Bm = _f(B[:K, :N]).t() if b_mn else _f(B[:N, :K])
+    off = _window_offset(win_state, window_rows, n_windows) if (win_state is not None and win_flags) else 0
+    a_off = off if (win_flags & 1) else 0
+    b_off = off if (win_flags & 2) else 0
+    l_off = off if (win_flags & 4) else 0
+    Am = _f(A[:K, :M]).t() if a_mn else _f(A[a_off: a_off + M, :K])
+    Bm = _f(B[b_off: b_off + K, :N]).t() if b_mn else _f(B[:N, :K])
     D = (Am @ Bm.t()) * alpha
     if bias is not None:
         D = D + _f(bias[:N])
@@ -39,6 +54,17 @@ def gemm_bf16(A, a_mn, B, b_mn, M, N, K, alpha: float = 1.0, bias=None, relu: bo
         D = torch.relu(D)
     if mask_src is not None:
         D = D * (_f(mask_src[:M, :N]) > 0)
+    if loss_kind:
+        if out_f32 is not None:
+            out_f32[:M, :N] = D
+        if loss_kind == 1:
+            lab = labels[l_off: l_off + M].to(torch.int64)
+            loss_slot[0] += F.cross_entropy(D, lab, reduction="sum") * loss_scale
+            D = (torch.softmax(D, 1) - F.one_hot(lab, N)) * loss_scale
+        else:
+            dlt = D - _f(target[l_off: l_off + M, :N])
+            loss_slot[0] += (dlt * dlt).sum() * loss_scale
+            D = 2.0 * dlt * loss_scale
     if colsum is not None:
         colsum[:N] += D.sum(0)
     if colsumsq is not None:
@@ -47,7 +73,7 @@ def gemm_bf16(A, a_mn, B, b_mn, M, N, K, alpha: float = 1.0, bias=None, relu: bo
         out_bf16[:M, :N] = D.to(out_bf16.dtype)
     if out_t_bf16 is not None:
         out_t_bf16[:N, :M] = D.t().to(out_t_bf16.dtype)
-    if out_f32 is not None:
+    if out_f32 is not None and not loss_kind:
         if atomic_f32:
             out_f32[:M, :N] += D
         else:
@@ -70,9 +96,11 @@ def _unfold_to(x_nchw: torch.Tensor, k: int, stride: int, pad: int, OH: int, OW:
 
 
 def im2col_nhwc(x, B, H, W, C, sb, sh, sw, sc, kh, kw, stride, pad, col, state=None, window_rows: int = 0, n_windows: int = 0):
-    """Generic-stride source, (c, i, j) column order (= torch's [Cout, Cin, kh, kw] weight layout)."""
-    assert state is None and kh == kw
-    src = torch.as_strided(x, (B, C, H, W), (sb, sc, sh, sw), x.storage_offset())
+    """Generic-stride source, (c, i, j) column order (= torch's [Cout, Cin, kh, kw] weight layout); with ``state`` the
+    samples are the current iteration's window of a resident partition."""
+    assert kh == kw
+    b_off = _window_offset(state, window_rows, n_windows) if state is not None else 0
+    src = torch.as_strided(x, (B, C, H, W), (sb, sc, sh, sw), x.storage_offset() + b_off * sb)
     OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     p = _unfold_to(_f(src), kh, stride, pad, OH, OW)           # [B, C, kk, L]
     col[: B * OH * OW, : C * kh * kw] = p.permute(0, 3, 1, 2).reshape(B * OH * OW, C * kh * kw).to(col.dtype)
@@ -88,6 +116,12 @@ def im2col_cl(x, B, H, W, C, kh, kw, stride, pad, dil, OH, OW, col):
         xn = xd
     p = _unfold_to(xn, kh, stride, pad, OH, OW)                # [B, C, kk, L]
     col[: B * OH * OW, : kh * kw * C] = p.permute(0, 3, 2, 1).reshape(B * OH * OW, kh * kw * C).to(col.dtype)
+
+
+def flip_conv_weight(w, Cout, Cin, kh, kw, out):
+    """[Cout, (ci, i, j)] -> [Cin, (co, kh-1-i, kw-1-j)]"""
+    w4 = w[:Cout, : Cin * kh * kw].reshape(Cout, Cin, kh, kw)
+    out[:Cin, : Cout * kh * kw] = w4.flip(2, 3).permute(1, 0, 2, 3).reshape(Cin, Cout * kh * kw)
 
 
 def flip_conv_weight_cl(w, Cout, Cin, kh, kw, out):
@@ -200,3 +234,51 @@ def softmax_ce(logits, labels, C, loss_slot, dz: Optional[torch.Tensor], dzt, db
             dzt[:C, :B] = g.t().to(dzt.dtype)
         if db is not None:
             db[:C] += g.sum(0)
+
+
+def mse_loss(pred, target, D, loss_slot, dz, dzt, db, pad_cols):
+    B = pred.shape[0]
+    dlt = _f(pred[:, :D]) - _f(target[:, :D])
+    loss_slot[0] += (dlt * dlt).mean()
+    g = 2.0 * dlt / (B * D)
+    if dz is not None:
+        dz[:, :D] = g.to(dz.dtype)
+    if dzt is not None:
+        dzt[:D, :B] = g.t().to(dzt.dtype)
+    if db is not None:
+        db[:D] += g.sum(0)
+
+
+def maxpool_dropout(backward, x_or_dx, ld_x, y_or_dy, idx, B, H, W, C, k, p_drop: float = 0.0, train: bool = False, seed: int = 0,
+                    state=None, y_nhwc: bool = False, relu_x=None, db=None):
+    """k x k / stride k max-pool (floor) over NHWC; the pooled map is written NHWC or in torch's flatten order
+    (c, ph, pw).  Dropout2d is only emulated as the identity (p_drop == 0 or evaluation)."""
+    if train and p_drop > 0:
+        raise NotImplementedError("reference maxpool_dropout: the kernel's counter-based channel dropout is not emulated")
+    PH, PW = H // k, W // k
+    if not backward:
+        xn = _f(x_or_dx[: B * H * W, :C]).reshape(B, H, W, C)[:, : PH * k, : PW * k]
+        win = xn.reshape(B, PH, k, PW, k, C).permute(0, 1, 3, 5, 2, 4).reshape(B, PH, PW, C, k * k)
+        best, arg = win.max(-1)
+        if y_nhwc:
+            y_or_dy[: B * PH * PW, :C] = best.reshape(B * PH * PW, C).to(y_or_dy.dtype)
+        else:
+            y_or_dy[:B, : C * PH * PW] = best.permute(0, 3, 1, 2).reshape(B, C * PH * PW).to(y_or_dy.dtype)
+        idx[: B * PH * PW * C] = arg.reshape(-1).to(torch.uint8)
+        return
+    if y_nhwc:
+        g = _f(y_or_dy[: B * PH * PW, :C]).reshape(B, PH, PW, C)
+    else:
+        g = _f(y_or_dy[:B, : C * PH * PW]).reshape(B, C, PH, PW).permute(0, 2, 3, 1)
+    arg = idx[: B * PH * PW * C].reshape(B, PH, PW, C).to(torch.int64)
+    onehot = F.one_hot(arg, k * k).to(torch.float32)                                # [B, PH, PW, C, kk]
+    if relu_x is not None:
+        xr = _f(relu_x[: B * H * W, :C]).reshape(B, H, W, C)[:, : PH * k, : PW * k]
+        xw = xr.reshape(B, PH, k, PW, k, C).permute(0, 1, 3, 5, 2, 4).reshape(B, PH, PW, C, k * k)
+        g = g * ((xw * onehot).sum(-1) > 0)
+    d = (onehot * g.unsqueeze(-1)).reshape(B, PH, PW, C, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, PH * k, PW * k, C)
+    dx = _f(x_or_dx[: B * H * W, :C]).reshape(B, H, W, C).clone()
+    dx[:, : PH * k, : PW * k] = d
+    x_or_dx[: B * H * W, :C] = dx.reshape(B * H * W, C).to(x_or_dx.dtype)
+    if db is not None:
+        db[:C] += g.sum((0, 1, 2))

@@ -33,11 +33,13 @@ class _EmulatedUpdater:
         apply_update_(o.spec, o.param, o.grad[: o.numel], o.opt_state, o.steps)
         o.loss_hist[o.steps - 1] = o.grad[o.numel]
         o.mailbox[1] = o.steps
+        o.state[4] = o.steps                  # StepState.iter: the batch window of the next step
         o.grad.zero_()
         self.publish()
 
 
 class EmulatedUpdate:
+    wants_segments = True          # plans built through ``backend_factory`` must still hand over their segment table
     use_multicast = False
     exchange = "emulated"
 

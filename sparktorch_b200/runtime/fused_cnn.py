@@ -190,10 +190,12 @@ class FusedCNN:
 
     def __init__(self, model: nn.Module, low: LoweredCNN, kind: str, spec, world: int, rank: int, device: torch.device,
                  batch: int, val_rows: int, patience: int, max_iters: int, seed: int = 0, backend_factory=None,
-                 inference: bool = False):
+                 inference: bool = False, ops=None, act_dtype: torch.dtype = torch.bfloat16):
+        """``ops`` / ``act_dtype`` (and a ``backend_factory`` whose product sets ``wants_segments``): CPU emulation hooks."""
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
-        self.C = native.load(required=True)
+        self.C = ops if ops is not None else native.load(required=True)
+        self.act_dtype = act_dtype
         self.device, self.world, self.rank = device, world, rank
         self.kind, self.low = kind, low
         self.lowered = low
@@ -253,7 +255,7 @@ class FusedCNN:
             peer = getattr(self.fu, "peer_table", None)
             self.peer_kw[id(m)] = dict(peer_table=peer, peer_shard_elems=self.fu.shard_elems, peer_w_off=wo, peer_bias_off=bo,
                                        peer_fill_local=True) if peer is not None else {}
-        if backend_factory is None:
+        if backend_factory is None or getattr(self.fu, "wants_segments", False):
             self.fu.build([seg_of[o] for o in sorted(seg_of)], zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]
         self.train_loss_slot = self.fu.grad[numel + 2: numel + 3]
@@ -263,17 +265,18 @@ class FusedCNN:
             if i > 0:
                 g = self.geo[i]
                 kflip = g["Cout"] * g["kh"] * g["kw"]
-                self.Wflip[i] = torch.zeros(g["Cin"], _pad(kflip), dtype=torch.bfloat16, device=device)[:, :kflip]
+                self.Wflip[i] = torch.zeros(g["Cin"], _pad(kflip), dtype=self.fu.wbf16.dtype, device=device)[:, :kflip]
         self.fuse_loss = dL <= 32 and os.environ.get("SPARKTORCH_FUSE_LOSS", "1") == "1"
         self.window = None
-        self.side = torch.cuda.Stream(device=device) if os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None
+        self.side = (torch.cuda.Stream(device=device)
+                     if device.type == "cuda" and os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None)
         self.train = self._alloc(batch, backward=not inference)
         self.val = self._alloc(val_rows, backward=False) if val_rows > 0 else None
         self.n_launch = 0
 
     # ------------------------------------------------------------------------------------------------
     def _alloc(self, rows: int, backward: bool):
-        dev, bf = self.device, torch.bfloat16
+        dev, bf = self.device, self.act_dtype
         buf = {"rows": rows, "acts": [torch.zeros(rows, _pad(self.d0), dtype=bf, device=dev)[:, : self.d0]]}
         buf["col"], buf["conv_out"], buf["pool_out"], buf["pool_idx"] = [], [], [], []
         buf["dconv"], buf["colT"], buf["dpool"] = [], [], []

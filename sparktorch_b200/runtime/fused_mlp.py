@@ -153,10 +153,14 @@ class FusedMLP:
     """Device buffers + enqueue functions of one replica."""
 
     def __init__(self, model: nn.Module, lowered: Lowered, kind: str, spec, world: int, rank: int,
-                 device: torch.device, batch: int, val_rows: int, patience: int, max_iters: int, backend_factory=None):
+                 device: torch.device, batch: int, val_rows: int, patience: int, max_iters: int, backend_factory=None,
+                 ops=None, act_dtype: torch.dtype = torch.bfloat16):
+        """``ops`` / ``act_dtype`` (and a ``backend_factory`` whose product sets ``wants_segments``) exist for the CPU
+        emulation of the plan (ops/reference.py, runtime/emulation.py); production: native extension, bf16."""
         from sparktorch_b200.parallel.p2p import FusedUpdate
 
-        self.C = native.load(required=True)
+        self.C = ops if ops is not None else native.load(required=True)
+        self.act_dtype = act_dtype
         self.device, self.world, self.rank = device, world, rank
         self.kind, self.lowered = kind, lowered
         self.B, self.nv = batch, val_rows
@@ -211,7 +215,7 @@ class FusedMLP:
                 self.peer_kw.append({})
         for o in sorted(seg_of):
             rows.append(seg_of[o])
-        if backend_factory is None:
+        if backend_factory is None or getattr(self.fu, "wants_segments", False):
             self.fu.build(rows, zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]          # tail[0]: rides in the all-reduce
         self.train_loss_slot = self.fu.grad[numel + 2: numel + 3]  # tail[2]: local record when validating
@@ -221,17 +225,18 @@ class FusedMLP:
         self.n_launch = 0
         self.fuse_loss = fuse_loss
         self.window = None            # (n_windows, window_rows): batch = window of the resident partition
-        self.side = torch.cuda.Stream(device=device) if os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None
+        self.side = (torch.cuda.Stream(device=device)
+                     if device.type == "cuda" and os.environ.get("SPARKTORCH_SIDE_STREAM", "1") == "1" else None)
 
     def _alloc_acts(self, rows: int, backward: bool):
-        d, L, dev = self.d, self.L, self.device
-        acts = [torch.zeros(rows, _pad(d[0]), dtype=torch.bfloat16, device=dev)[:, : d[0]]]
+        d, L, dev, adt = self.d, self.L, self.device, self.act_dtype
+        acts = [torch.zeros(rows, _pad(d[0]), dtype=adt, device=dev)[:, : d[0]]]
         for l in range(1, L):
-            acts.append(torch.zeros(rows, _pad(d[l]), dtype=torch.bfloat16, device=dev)[:, : d[l]])
+            acts.append(torch.zeros(rows, _pad(d[l]), dtype=adt, device=dev)[:, : d[l]])
         logits = torch.zeros(rows, _pad(d[L], 16), dtype=torch.float32, device=dev)[:, : d[L]]
         dz = None
         if backward:
-            dz = [None] + [torch.zeros(rows, _pad(d[l]), dtype=torch.bfloat16, device=dev)[:, : d[l]] for l in range(1, L + 1)]
+            dz = [None] + [torch.zeros(rows, _pad(d[l]), dtype=adt, device=dev)[:, : d[l]] for l in range(1, L + 1)]
         if self.kind == "ce":
             tgt = torch.zeros(rows, dtype=torch.int32, device=dev)
         else:
@@ -303,8 +308,8 @@ class FusedMLP:
         """dgrad chain on the current stream; the weight-gradient GEMMs only feed the update kernel, so
         they run on a side stream (forked/joined with events, captured into the same graph)."""
         acts, dz, d, L, rows = buf["acts"], buf["dz"], self.d, self.L, buf["rows"]
-        main = torch.cuda.current_stream(self.device)
         side = self.side if (self.side is not None and L > 1) else None
+        main = torch.cuda.current_stream(self.device) if side is not None else None
         for l in range(L, 0, -1):
             # wgrad: dW_l[d_l, d_{l-1}] = dZ_l^T A_{l-1}  (reduction over the batch; both operands MN-major)
             sk = self._split_k(d[l], d[l - 1], rows)

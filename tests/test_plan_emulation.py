@@ -102,3 +102,143 @@ def test_resnet_plan_inference_uses_running_statistics():
     torch.testing.assert_close(plan.train["logits"], want, rtol=1e-3, atol=1e-4)
     for (n1, b1), (_n2, b2) in zip(model.named_buffers(), ref.named_buffers()):
         torch.testing.assert_close(b1, b2, rtol=0, atol=0)          # evaluation never touches the statistics
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# MLP and CNN plans
+from sparktorch_b200.runtime.fused_cnn import FusedCNN, lower_cnn  # noqa: E402
+from sparktorch_b200.runtime.fused_mlp import FusedMLP, lower_mlp, loss_kind  # noqa: E402
+
+
+def _emulated(plan_cls, model, low, kind, spec, batch, **kw):
+    return plan_cls(model, low, kind, spec, 1, 0, torch.device("cpu"), batch, 0, 0, 16,
+                    backend_factory=lambda numel, wb: EmulatedUpdate(numel, spec, wb), ops=reference, act_dtype=torch.float32, **kw)
+
+
+def _compare_steps(plan, model, ref, ref_opt, crit, batches, windowed=False, steps_tight=3):
+    got = dict(model.named_parameters())
+    for step, (x, y) in enumerate(batches):
+        if not windowed:
+            plan.train["acts"][0].copy_(x)
+            plan.train["tgt"].copy_(y if plan.kind != "ce" else y.to(torch.int32))
+        plan.forward(plan.train, slot=plan.loss_slot, train=True, windowed=windowed)
+        plan.backward(plan.train, windowed=windowed)
+        ref_opt.zero_grad()
+        out = ref(x)
+        loss = crit(out, y)
+        loss.backward()
+        assert abs(float(plan.loss_slot[0]) - float(loss.detach())) < 1e-4 * max(1.0, abs(float(loss.detach()))), (step, float(plan.loss_slot[0]), float(loss))
+        for name, p in ref.named_parameters():
+            torch.testing.assert_close(got[name].grad, p.grad, rtol=1e-3, atol=1e-5, msg=lambda m, n=name, s=step: f"step {s} {n}: {m}")
+        plan.update()
+        ref_opt.step()
+        for name, p in ref.named_parameters():
+            torch.testing.assert_close(got[name].detach(), p.detach(), rtol=1e-3, atol=1e-5, msg=lambda m, n=name, s=step: f"step {s} {n}: {m}")
+
+
+@pytest.mark.parametrize("fuse_loss", ["1", "0"])
+def test_mlp_plan_cross_entropy_adam(monkeypatch, fuse_loss):
+    monkeypatch.setenv("SPARKTORCH_FUSE_LOSS", fuse_loss)
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(20, 24), nn.ReLU(), nn.Linear(24, 24), nn.ReLU(), nn.Linear(24, 5))
+    ref = copy.deepcopy(model)
+    kw = {"lr": 1e-2, "weight_decay": 1e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_mlp(model)
+    plan = _emulated(FusedMLP, model, low, loss_kind(nn.CrossEntropyLoss(), low), spec, 12)
+    assert plan.fuse_loss == (fuse_loss == "1")
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(12, 20, generator=g), torch.randint(0, 5, (12,), generator=g)) for _ in range(4)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
+
+
+def test_mlp_plan_mse_sgd_momentum_no_bias():
+    torch.manual_seed(1)
+    model = nn.Sequential(nn.Linear(10, 16, bias=False), nn.ReLU(), nn.Linear(16, 3))
+    ref = copy.deepcopy(model)
+    kw = {"lr": 0.05, "momentum": 0.9, "nesterov": True}
+    spec = parse_optimizer(torch.optim.SGD, kw)
+    low = lower_mlp(model)
+    plan = _emulated(FusedMLP, model, low, loss_kind(nn.MSELoss(), low), spec, 9)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randn(9, 10, generator=g), torch.randn(9, 3, generator=g)) for _ in range(4)]
+    _compare_steps(plan, model, ref, torch.optim.SGD(ref.parameters(), **kw), nn.MSELoss(), batches)
+
+
+def test_mlp_plan_batch_windows_follow_the_device_iteration_counter():
+    """'sweep' sampling: the GEMMs address window (iter % n_windows) of the resident partition themselves."""
+    torch.manual_seed(2)
+    model = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 4))
+    ref = copy.deepcopy(model)
+    kw = {"lr": 1e-2}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_mlp(model)
+    B, windows = 6, 3
+    plan = _emulated(FusedMLP, model, low, "ce", spec, B)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(5)
+    X, Y = torch.randn(B * windows, 8, generator=g), torch.randint(0, 4, (B * windows,), generator=g)
+    plan.train["acts"][0] = X.clone()                     # the resident partition IS the first operand
+    plan.train["tgt"] = Y.to(torch.int32)
+    plan.window = (windows, B)
+    batches = [(X[(i % windows) * B: (i % windows + 1) * B], Y[(i % windows) * B: (i % windows + 1) * B]) for i in range(5)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches, windowed=True)
+
+
+class _ConvNet(nn.Module):
+    """conv-relu-pool, conv-relu (no pool), conv-relu-pool, flatten, two Linear layers."""
+
+    def __init__(self):
+        super().__init__()
+        self.c1 = nn.Conv2d(1, 8, 3, padding=1)
+        self.c2 = nn.Conv2d(8, 16, 3)
+        self.c3 = nn.Conv2d(16, 16, 3, padding=1)
+        self.f1 = nn.Linear(16 * 2 * 2, 20)
+        self.f2 = nn.Linear(20, 6)
+
+    def forward(self, x):
+        x = x.view(-1, 1, 12, 12)
+        x = nn.functional.max_pool2d(torch.relu(self.c1(x)), 2)      # 8 x 6 x 6
+        x = torch.relu(self.c2(x))                                   # 16 x 4 x 4
+        x = nn.functional.max_pool2d(torch.relu(self.c3(x)), 2)      # 16 x 2 x 2
+        x = torch.flatten(x, 1)
+        return self.f2(torch.relu(self.f1(x)))
+
+
+@pytest.mark.parametrize("fuse_loss", ["1", "0"])
+def test_cnn_plan_matches_autograd(monkeypatch, fuse_loss):
+    monkeypatch.setenv("SPARKTORCH_FUSE_LOSS", fuse_loss)
+    torch.manual_seed(3)
+    model = _ConvNet()
+    ref = copy.deepcopy(model)
+    kw = {"lr": 5e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_cnn(model, 144)
+    assert low is not None and [c.pool for c in low.convs] == [2, 0, 2]
+    plan = _emulated(FusedCNN, model, low, "ce", spec, 7)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(6)
+    batches = [(torch.randn(7, 144, generator=g), torch.randint(0, 6, (7,), generator=g)) for _ in range(3)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
+
+
+def test_mnist_cnn_plan_without_dropout_matches_autograd():
+    from sparktorch_b200.models import MnistCNN
+
+    torch.manual_seed(4)
+    model = MnistCNN()
+    for m in model.modules():
+        if isinstance(m, (nn.Dropout, nn.Dropout2d)):
+            m.p = 0.0                                                # the counter-based dropout mask is not emulated
+    ref = copy.deepcopy(model)
+    kw = {"lr": 1e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_cnn(model, 784)
+    assert low is not None
+    plan = _emulated(FusedCNN, model, low, "ce", spec, 4)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(4, 784, generator=g), torch.randint(0, 10, (4,), generator=g)) for _ in range(2)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
