@@ -216,9 +216,11 @@ def run_ours(args):
         "config": {"model": MODEL_NAME[args.model], "global_batch": gb, "seq_len": IN_FEATURES,
                    "parallelism": f"dp{args.gpus}", "per_gpu_batch": args.batch, "mode": args.mode,
                    "engine": h.get("engine"), "comm": h.get("comm"), "sampling": h.get("sampling"),
-                   "l2": f"inputs larger than L2: resident partition {rows}x{IN_FEATURES} per GPU "
-                         f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
-                         "weights/optimizer state stay cache resident as in any training loop"},
+                   "l2": (("inputs larger than L2" if rows * IN_FEATURES * 2 > 126 * 2**20 else
+                           "WARNING inputs smaller than L2 (raise --rows-per-gpu)") +
+                          f": resident partition {rows}x{IN_FEATURES} per GPU "
+                          f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
+                          "weights/optimizer state stay cache resident as in any training loop")},
         "gpu_launches": int(h.get("gpu_launches_per_step", 0) * args.steps),
         "clocks": clock_summary(h),
     }

@@ -94,3 +94,28 @@ def test_progress_watchdog_fires_on_stall_and_stays_quiet_on_progress():
     with ProgressWatchdog(lambda: 0, timeout_s=0, on_stall=quiet.append):    # disabled
         time.sleep(0.1)
     assert not quiet
+
+
+def test_bench_contract_on_cpu():
+    """bench.py prints ONE JSON line with the keys the driver parses (CPU run of the eager engine)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--device", "cpu", "--steps", "3", "--warmup", "3",
+                          "--rows-per-gpu", "1024"], capture_output=True, text=True, timeout=600, cwd=root)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
+        assert k in r, k
+    assert r["n_gpus"] == 1 and r["steps"] == 3 and r["warmup"] == 3 and r["higher_is_better"] is True and r["scaling"] == "weak"
+    assert r["value"] > 0 and abs(r["value"] - 256 * 3 / (r["ms_per_step"] * 3 / 1e3)) / r["value"] < 1e-6
+    for k in ("model", "global_batch", "seq_len", "parallelism"):
+        assert k in r["config"], k
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in r["e2e"], k
+    assert r["config"]["l2"].startswith("WARNING")          # 1024 rows do not exceed L2 and the line says so
