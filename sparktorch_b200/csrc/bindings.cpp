@@ -99,27 +99,33 @@ void gemm_bf16(const Tensor& A, bool a_mn, const Tensor& B, bool b_mn, int64_t M
         "gemm_bf16");
 }
 
+static const st::StepState* win_ptr(const OptT& win_state) {
+  return win_state ? reinterpret_cast<const st::StepState*>(win_state->data_ptr()) : nullptr;
+}
+
+// win_state/window_rows/n_windows: labels (targets) are the resident partition's, the batch is the current window
 void softmax_ce(const Tensor& logits, const Tensor& labels, int64_t C, const Tensor& loss_slot, const OptT& dz,
-                const OptT& dzt, const OptT& db, int64_t pad_cols) {
+                const OptT& dzt, const OptT& db, int64_t pad_cols, const OptT& win_state, int64_t window_rows, int64_t n_windows) {
   req_2d(logits, at::kFloat, "logits");
   TORCH_CHECK(labels.scalar_type() == at::kInt && loss_slot.scalar_type() == at::kFloat);
+  TORCH_CHECK(labels.numel() >= (win_state ? std::max<int64_t>(1, n_windows) * window_rows : logits.size(0)), "labels too short");
   c10::cuda::CUDAGuard guard(logits.device());
   check(st::softmax_ce(logits.data_ptr<float>(), logits.stride(0), labels.data_ptr<int32_t>(), int(logits.size(0)), int(C),
                        loss_slot.data_ptr<float>(), dz ? bf16pm(*dz) : nullptr, dz ? dz->stride(0) : 0,
                        dzt ? bf16pm(*dzt) : nullptr, dzt ? dzt->stride(0) : 0, db ? db->data_ptr<float>() : nullptr,
-                       int(pad_cols), cur_stream()),
+                       int(pad_cols), cur_stream(), win_ptr(win_state), window_rows, n_windows),
         "softmax_ce");
 }
 
 void mse_loss(const Tensor& pred, const Tensor& target, int64_t D, const Tensor& loss_slot, const OptT& dz, const OptT& dzt,
-              const OptT& db, int64_t pad_cols) {
+              const OptT& db, int64_t pad_cols, const OptT& win_state, int64_t window_rows, int64_t n_windows) {
   req_2d(pred, at::kFloat, "pred");
   req_2d(target, at::kFloat, "target");
   c10::cuda::CUDAGuard guard(pred.device());
   check(st::mse_loss(pred.data_ptr<float>(), pred.stride(0), target.data_ptr<float>(), target.stride(0), int(pred.size(0)),
                      int(D), loss_slot.data_ptr<float>(), dz ? bf16pm(*dz) : nullptr, dz ? dz->stride(0) : 0,
                      dzt ? bf16pm(*dzt) : nullptr, dzt ? dzt->stride(0) : 0, db ? db->data_ptr<float>() : nullptr, int(pad_cols),
-                     cur_stream()),
+                     cur_stream(), win_ptr(win_state), window_rows, n_windows),
         "mse_loss");
 }
 
@@ -557,8 +563,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("peer_w_off") = 0, py::arg("peer_bias_off") = -1, py::arg("peer_fill_local") = false,
         py::arg("push_table") = py::none(), py::arg("push_me") = 0, py::arg("push_mask") = 0,
         py::arg("push_state") = py::none(), py::arg("colsumsq") = py::none());
-  m.def("softmax_ce", &softmax_ce);
-  m.def("mse_loss", &mse_loss);
+  m.def("softmax_ce", &softmax_ce, py::arg("logits"), py::arg("labels"), py::arg("C"), py::arg("loss_slot"), py::arg("dz"), py::arg("dzt"),
+        py::arg("db"), py::arg("pad_cols"), py::arg("win_state") = py::none(), py::arg("window_rows") = 0, py::arg("n_windows") = 1);
+  m.def("mse_loss", &mse_loss, py::arg("pred"), py::arg("target"), py::arg("D"), py::arg("loss_slot"), py::arg("dz"), py::arg("dzt"),
+        py::arg("db"), py::arg("pad_cols"), py::arg("win_state") = py::none(), py::arg("window_rows") = 0, py::arg("n_windows") = 1);
   m.def("gather_batch", &gather_batch);
   m.def("transpose_bf16", &transpose_bf16);
   m.def("im2col_nhwc", &im2col_nhwc, py::arg("x"), py::arg("B"), py::arg("H"), py::arg("W"), py::arg("C"), py::arg("sb"),

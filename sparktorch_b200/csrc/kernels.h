@@ -12,10 +12,10 @@ extern int g_persistent_mode;   // GEMM: 0 never persistent, 1 auto (tiles > #SM
 // ---- loss.cu
 int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,
                __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
-               cudaStream_t stream);
+               cudaStream_t stream, const struct StepState* win_state = nullptr, int64_t window_rows = 0, int64_t n_windows = 1);
 int mse_loss(const float* pred, int64_t ldp, const float* target, int64_t ldt, int B, int D, float* loss_slot,
              __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
-             cudaStream_t stream);
+             cudaStream_t stream, const struct StepState* win_state = nullptr, int64_t window_rows = 0, int64_t n_windows = 1);
 
 // ---- data.cu
 struct StepState {            // lives in device memory, advanced by the update kernel

@@ -18,12 +18,15 @@ constexpr int MAX_SMEM_CLASSES = 2048;
 __global__ void __launch_bounds__(LOSS_THREADS)
 softmax_ce_kernel(const float* __restrict__ logits, int64_t ldz, const int32_t* __restrict__ labels, int B, int C,
                   float* __restrict__ loss_slot, __nv_bfloat16* __restrict__ dz, int64_t ld_dz,
-                  __nv_bfloat16* __restrict__ dzt, int64_t ld_dzt, float* __restrict__ db, int pad_cols) {
+                  __nv_bfloat16* __restrict__ dzt, int64_t ld_dzt, float* __restrict__ db, int pad_cols,
+                  const StepState* __restrict__ win_state, int64_t window_rows, int64_t n_windows) {
   __shared__ float s_db[MAX_SMEM_CLASSES];
   __shared__ float s_loss;
   const bool want_db = db != nullptr && C <= MAX_SMEM_CLASSES;
   pdl_wait();
   pdl_launch_dependents();
+  // labels of the resident partition: the batch is the window of the current iteration (same rule as GemmWindow)
+  if (win_state != nullptr) labels += (win_state->iter % n_windows) * window_rows;
   for (int c = threadIdx.x; c < C && want_db; c += blockDim.x) s_db[c] = 0.f;
   if (threadIdx.x == 0) s_loss = 0.f;
   __syncthreads();
@@ -71,12 +74,14 @@ softmax_ce_kernel(const float* __restrict__ logits, int64_t ldz, const int32_t* 
 __global__ void __launch_bounds__(LOSS_THREADS)
 mse_kernel(const float* __restrict__ pred, int64_t ldp, const float* __restrict__ target, int64_t ldt, int B, int D,
            float* __restrict__ loss_slot, __nv_bfloat16* __restrict__ dz, int64_t ld_dz, __nv_bfloat16* __restrict__ dzt,
-           int64_t ld_dzt, float* __restrict__ db, int pad_cols) {
+           int64_t ld_dzt, float* __restrict__ db, int pad_cols, const StepState* __restrict__ win_state, int64_t window_rows,
+           int64_t n_windows) {
   __shared__ float s_db[MAX_SMEM_CLASSES];
   __shared__ float s_loss;
   const bool want_db = db != nullptr && D <= MAX_SMEM_CLASSES;
   pdl_wait();
   pdl_launch_dependents();
+  if (win_state != nullptr) target += (win_state->iter % n_windows) * window_rows * ldt;
   for (int c = threadIdx.x; c < D && want_db; c += blockDim.x) s_db[c] = 0.f;
   if (threadIdx.x == 0) s_loss = 0.f;
   __syncthreads();
@@ -116,16 +121,18 @@ static int grid_for(int64_t work_items, int per_block) {
 
 int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,
                __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
-               cudaStream_t stream) {
+               cudaStream_t stream, const StepState* win_state, int64_t window_rows, int64_t n_windows) {
+  if (n_windows < 1) n_windows = 1;
   return int(launch_kernel(softmax_ce_kernel, dim3(grid_for(B, LOSS_THREADS / 32)), dim3(LOSS_THREADS), 0, stream, logits, ldz,
-                           labels, B, C, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols));
+                           labels, B, C, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols, win_state, window_rows, n_windows));
 }
 
 int mse_loss(const float* pred, int64_t ldp, const float* target, int64_t ldt, int B, int D, float* loss_slot,
              __nv_bfloat16* dz, int64_t ld_dz, __nv_bfloat16* dzt, int64_t ld_dzt, float* db, int pad_cols,
-             cudaStream_t stream) {
+             cudaStream_t stream, const StepState* win_state, int64_t window_rows, int64_t n_windows) {
+  if (n_windows < 1) n_windows = 1;
   return int(launch_kernel(mse_kernel, dim3(grid_for(int64_t(B) * pad_cols, LOSS_THREADS)), dim3(LOSS_THREADS), 0, stream, pred,
-                           ldp, target, ldt, B, D, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols));
+                           ldp, target, ldt, B, D, loss_slot, dz, ld_dz, dzt, ld_dzt, db, pad_cols, win_state, window_rows, n_windows));
 }
 
 }  // namespace st

@@ -221,10 +221,12 @@ def avgpool_cl(backward, x_or_dx, y_or_dy, B, HW, C):
         x_or_dx[: B * HW, :C] = (_f(y_or_dy[:B, :C]) / HW).repeat_interleave(HW, 0).to(x_or_dx.dtype)
 
 
-def softmax_ce(logits, labels, C, loss_slot, dz: Optional[torch.Tensor], dzt, db, pad_cols):
+def softmax_ce(logits, labels, C, loss_slot, dz: Optional[torch.Tensor], dzt, db, pad_cols, win_state=None, window_rows: int = 0,
+               n_windows: int = 1):
     B = logits.shape[0]
     z = _f(logits[:, :C])
-    lab = labels.to(torch.int64)
+    off = _window_offset(win_state, window_rows, n_windows) if win_state is not None else 0
+    lab = labels[off: off + B].to(torch.int64)
     loss_slot[0] += F.cross_entropy(z, lab, reduction="mean")
     if dz is not None or dzt is not None or db is not None:
         g = (torch.softmax(z, 1) - F.one_hot(lab, C)) / B
@@ -236,9 +238,10 @@ def softmax_ce(logits, labels, C, loss_slot, dz: Optional[torch.Tensor], dzt, db
             db[:C] += g.sum(0)
 
 
-def mse_loss(pred, target, D, loss_slot, dz, dzt, db, pad_cols):
+def mse_loss(pred, target, D, loss_slot, dz, dzt, db, pad_cols, win_state=None, window_rows: int = 0, n_windows: int = 1):
     B = pred.shape[0]
-    dlt = _f(pred[:, :D]) - _f(target[:, :D])
+    off = _window_offset(win_state, window_rows, n_windows) if win_state is not None else 0
+    dlt = _f(pred[:, :D]) - _f(target[off: off + B, :D])
     loss_slot[0] += (dlt * dlt).mean()
     g = 2.0 * dlt / (B * D)
     if dz is not None:

@@ -395,7 +395,10 @@ class FusedCNN:
             dz = buf["dz"][self.L] if train else None
             db = self.gb[id(low.linears[-1].module)] if train else None
             fn = self.C.softmax_ce if self.kind == "ce" else self.C.mse_loss
-            fn(buf["logits"], buf["tgt"], self.dl[-1], slot, dz, None, db, _pad(self.dl[-1]))
+            lw = {}
+            if windowed and self.window is not None:      # labels of the resident partition: same window as the images
+                lw = dict(win_state=self.fu.state, window_rows=self.window[1], n_windows=self.window[0])
+            fn(buf["logits"], buf["tgt"], self.dl[-1], slot, dz, None, db, _pad(self.dl[-1]), **lw)
             self.n_launch += 1
 
     def _deep_head(self, rows: int) -> bool:

@@ -242,3 +242,47 @@ def test_mnist_cnn_plan_without_dropout_matches_autograd():
     g = torch.Generator().manual_seed(7)
     batches = [(torch.randn(4, 784, generator=g), torch.randint(0, 10, (4,), generator=g)) for _ in range(2)]
     _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
+
+
+def test_cnn_plan_split_head_reads_labels_of_the_current_window():
+    """MnistCNN's 3872-wide head takes the split-K + stand-alone loss path; with 'sweep' windows the loss kernel must read
+    the labels of the SAME window the im2col reads the images from."""
+    from sparktorch_b200.models import MnistCNN
+
+    torch.manual_seed(5)
+    model = MnistCNN(p_drop=0.0)
+    ref = copy.deepcopy(model)
+    kw = {"lr": 1e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_cnn(model, 784)
+    B, windows = 4, 3
+    plan = _emulated(FusedCNN, model, low, "ce", spec, B)
+    assert plan._deep_head(B)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(8)
+    X, Y = torch.randn(B * windows, 784, generator=g), torch.randint(0, 10, (B * windows,), generator=g)
+    plan.train["acts"][0] = X.clone()
+    plan.train["tgt"] = Y.to(torch.int32)
+    plan.window = (windows, B)
+    batches = [(X[(i % windows) * B: (i % windows + 1) * B], Y[(i % windows) * B: (i % windows + 1) * B]) for i in range(4)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches, windowed=True)
+
+
+def test_cnn_plan_fused_loss_with_batch_windows():
+    torch.manual_seed(6)
+    model = _ConvNet()
+    ref = copy.deepcopy(model)
+    kw = {"lr": 5e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_cnn(model, 144)
+    B, windows = 5, 4
+    plan = _emulated(FusedCNN, model, low, "ce", spec, B)
+    assert plan.fuse_loss and not plan._deep_head(B)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(9)
+    X, Y = torch.randn(B * windows, 144, generator=g), torch.randint(0, 6, (B * windows,), generator=g)
+    plan.train["acts"][0] = X.clone()
+    plan.train["tgt"] = Y.to(torch.int32)
+    plan.window = (windows, B)
+    batches = [(X[(i % windows) * B: (i % windows + 1) * B], Y[(i % windows) * B: (i % windows + 1) * B]) for i in range(6)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches, windowed=True)
