@@ -208,6 +208,33 @@ def test_softmax_ce_kernel(C):
     torch.testing.assert_close(l2[0], ref.detach(), rtol=1e-5, atol=1e-5)
 
 
+def test_loss_kernels_read_targets_of_the_current_window(C):
+    """'sweep' batches: labels / targets stay in the resident partition, the kernel offsets them by the device-side
+    iteration counter exactly like the GEMM batch windows."""
+    from sparktorch_b200.ops import reference
+
+    Bt, Cn, windows, it = 8, 10, 3, 5
+    state = torch.zeros(C.step_state_bytes() // 4, dtype=torch.int32, device=dev())
+    state[4] = it                                               # StepState.iter
+    off = (it % windows) * Bt
+    z = torch.randn(Bt, 16, device=dev())[:, :Cn]
+    y_all = torch.randint(0, Cn, (Bt * windows,), device=dev(), dtype=torch.int32)
+    loss = torch.zeros(1, device=dev())
+    dz = torch.zeros(Bt, 16, dtype=torch.bfloat16, device=dev())
+    C.softmax_ce(z, y_all, Cn, loss, dz, None, None, 16, win_state=state, window_rows=Bt, n_windows=windows)
+    ref = torch.nn.functional.cross_entropy(z, y_all[off: off + Bt].long())
+    torch.testing.assert_close(loss[0], ref, rtol=1e-5, atol=1e-5)
+    l_ref, dz_ref = torch.zeros(1), torch.zeros(Bt, 16)
+    reference.softmax_ce(z.cpu(), y_all.cpu(), Cn, l_ref, dz_ref, None, None, 16, win_state=state.cpu(), window_rows=Bt, n_windows=windows)
+    torch.testing.assert_close(dz.float().cpu(), dz_ref, rtol=1e-2, atol=1e-5)
+    D = 3
+    p = torch.randn(Bt, 8, device=dev())[:, :D]
+    t_all = torch.randn(Bt * windows, D, device=dev())
+    l2 = torch.zeros(1, device=dev())
+    C.mse_loss(p, t_all, D, l2, None, None, None, 8, win_state=state, window_rows=Bt, n_windows=windows)
+    torch.testing.assert_close(l2[0], torch.nn.functional.mse_loss(p, t_all[off: off + Bt]), rtol=1e-5, atol=1e-6)
+
+
 def test_mse_kernel(C):
     Bt, D = 200, 3
     p = torch.randn(Bt, 8, device=dev())[:, :D]
