@@ -483,7 +483,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0);
       if constexpr (CHUNK == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
-      const bool vec_ok = (col0 + CHUNK <= N);   // leading dims are multiples of 8 elements, col0 multiple of 16
 #pragma unroll
       for (int v = 0; v < 4; ++v) mk[v] = mk_next[v];
       if (col0 + CHUNK < N) load_mask(mk_next, col0 + CHUNK);   // prefetch the next chunk's mask
