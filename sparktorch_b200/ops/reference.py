@@ -252,17 +252,44 @@ def mse_loss(pred, target, D, loss_slot, dz, dzt, db, pad_cols, win_state=None, 
         db[:D] += g.sum(0)
 
 
+def dropout2d_keep_mask(seed: int, iteration: int, B: int, C: int, p_drop: float) -> torch.Tensor:
+    """The kernel's counter-based channel dropout (csrc/conv.cu ``hash3``): [B, C] bool, True = channel kept.
+    A pure function of (seed, iteration, sample, channel), so forward and backward agree without storing a mask and a
+    test can apply the very same mask to an autograd model."""
+    import numpy as np
+
+    M = 0xFFFFFFFF
+    a = np.uint64((int(seed) + int(iteration) * 0x632BE5AB) & M)
+    b = np.arange(B, dtype=np.uint64).reshape(B, 1)
+    c = np.arange(C, dtype=np.uint64).reshape(1, C)
+    x = ((a * np.uint64(0x9E3779B1)) & np.uint64(M)) ^ (((b + np.uint64(0x7F4A7C15)) & np.uint64(M)) * np.uint64(0x85EBCA77) & np.uint64(M)) \
+        ^ (((c + np.uint64(0x165667B1)) & np.uint64(M)) * np.uint64(0xC2B2AE3D) & np.uint64(M))
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & np.uint64(M)
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & np.uint64(M)
+    x ^= x >> np.uint64(16)
+    thresh = np.uint64(int(float(p_drop) * 4294967296.0)) if p_drop > 0 else np.uint64(0)
+    return torch.from_numpy(x >= thresh)
+
+
 def maxpool_dropout(backward, x_or_dx, ld_x, y_or_dy, idx, B, H, W, C, k, p_drop: float = 0.0, train: bool = False, seed: int = 0,
                     state=None, y_nhwc: bool = False, relu_x=None, db=None):
-    """k x k / stride k max-pool (floor) over NHWC; the pooled map is written NHWC or in torch's flatten order
-    (c, ph, pw).  Dropout2d is only emulated as the identity (p_drop == 0 or evaluation)."""
-    if train and p_drop > 0:
-        raise NotImplementedError("reference maxpool_dropout: the kernel's counter-based channel dropout is not emulated")
+    """k x k / stride k max-pool (floor) over NHWC, then dropout2d (whole channels of a sample zeroed, survivors scaled by
+    1/(1-p)); the pooled map is written NHWC or in torch's flatten order (c, ph, pw)."""
+    drop_on = bool(train and p_drop > 0)
+    keep = None
+    if drop_on:
+        it = (int(state[4]) + (int(state[5]) << 32)) if state is not None else 0
+        keep = dropout2d_keep_mask(seed, it, B, C, p_drop).view(B, 1, 1, C).to(torch.float32)
+    keep_scale = 1.0 / (1.0 - p_drop) if drop_on else 1.0
     PH, PW = H // k, W // k
     if not backward:
         xn = _f(x_or_dx[: B * H * W, :C]).reshape(B, H, W, C)[:, : PH * k, : PW * k]
         win = xn.reshape(B, PH, k, PW, k, C).permute(0, 1, 3, 5, 2, 4).reshape(B, PH, PW, C, k * k)
         best, arg = win.max(-1)
+        if drop_on:
+            best = best * keep * keep_scale
         if y_nhwc:
             y_or_dy[: B * PH * PW, :C] = best.reshape(B * PH * PW, C).to(y_or_dy.dtype)
         else:
@@ -274,6 +301,8 @@ def maxpool_dropout(backward, x_or_dx, ld_x, y_or_dy, idx, B, H, W, C, k, p_drop
     else:
         g = _f(y_or_dy[:B, : C * PH * PW]).reshape(B, C, PH, PW).permute(0, 2, 3, 1)
     arg = idx[: B * PH * PW * C].reshape(B, PH, PW, C).to(torch.int64)
+    if drop_on:
+        g = g * keep * keep_scale
     onehot = F.one_hot(arg, k * k).to(torch.float32)                                # [B, PH, PW, C, kk]
     if relu_x is not None:
         xr = _f(relu_x[: B * H * W, :C]).reshape(B, H, W, C)[:, : PH * k, : PW * k]

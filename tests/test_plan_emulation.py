@@ -286,3 +286,51 @@ def test_cnn_plan_fused_loss_with_batch_windows():
     plan.window = (windows, B)
     batches = [(X[(i % windows) * B: (i % windows + 1) * B], Y[(i % windows) * B: (i % windows + 1) * B]) for i in range(6)]
     _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches, windowed=True)
+
+
+def test_mnist_cnn_plan_with_counter_based_dropout2d():
+    """Dropout2d in the fused plan is a pure function of (seed, iteration, sample, channel).  Applying the same keep
+    mask to an autograd copy of the network must give the same loss, gradients and updates."""
+    from sparktorch_b200.models import MnistCNN
+
+    class MaskedDrop(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mask = None
+
+        def forward(self, x):
+            return x * self.mask
+
+    torch.manual_seed(7)
+    model = MnistCNN(p_drop=0.25)
+    ref = copy.deepcopy(model)
+    ref.drop = MaskedDrop()
+    kw = {"lr": 1e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    low = lower_cnn(model, 784)
+    assert low.convs[-1].p_drop == 0.25
+    B, seed = 6, 11
+    plan = _emulated(FusedCNN, model, low, "ce", spec, B, seed=seed)
+    plan.fu.updater.publish()
+    ref_opt = torch.optim.Adam(ref.parameters(), **kw)
+    g = torch.Generator().manual_seed(10)
+    got = dict(model.named_parameters())
+    kept = []
+    for step in range(3):
+        x, y = torch.randn(B, 784, generator=g), torch.randint(0, 10, (B,), generator=g)
+        keep = reference.dropout2d_keep_mask(seed + 1000003 * (len(low.convs) - 1), step, B, 32, 0.25)
+        kept.append(float(keep.float().mean()))
+        ref.drop.mask = (keep.float() / 0.75).view(B, 32, 1, 1)
+        plan.train["acts"][0].copy_(x)
+        plan.train["tgt"].copy_(y.to(torch.int32))
+        plan.forward(plan.train, slot=plan.loss_slot, train=True)
+        plan.backward(plan.train)
+        ref_opt.zero_grad()
+        loss = nn.functional.cross_entropy(ref(x), y)
+        loss.backward()
+        assert abs(float(plan.loss_slot[0]) - float(loss.detach())) < 1e-4
+        for name, p in ref.named_parameters():
+            torch.testing.assert_close(got[name].grad, p.grad, rtol=1e-3, atol=1e-5, msg=lambda m, n=name: f"{n}: {m}")
+        plan.update()
+        ref_opt.step()
+    assert 0.5 < sum(kept) / len(kept) < 0.95 and len(set(kept)) > 1        # masks vary per iteration, ~75 % kept
