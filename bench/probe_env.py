@@ -2,7 +2,6 @@
 import ctypes
 import os
 import subprocess
-import sys
 
 import torch
 

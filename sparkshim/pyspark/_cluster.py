@@ -33,7 +33,7 @@ import sys
 import threading
 import time
 import traceback
-from multiprocessing.connection import Client, Listener
+from multiprocessing.connection import Listener
 from typing import Any, Callable, List, Optional
 
 import cloudpickle

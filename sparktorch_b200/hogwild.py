@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import http.client
 import json
-import struct
 from typing import Dict, List
 
 import dill

@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 
 from sparktorch_b200.runtime.flat import FlatArena
-from sparktorch_b200.runtime.optim import OptSpec, parse_optimizer
+from sparktorch_b200.runtime.optim import parse_optimizer
 from sparktorch_b200.util import criterion_wants_class_index, split_validation
 
 

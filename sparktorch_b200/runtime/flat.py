@@ -13,7 +13,7 @@ slots at the end that ride in the same collective:
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import torch
 import torch.nn as nn

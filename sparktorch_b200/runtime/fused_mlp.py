@@ -32,7 +32,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from sparktorch_b200.ops import native
-from sparktorch_b200.runtime.flat import TAIL, FlatArena
+from sparktorch_b200.runtime.flat import FlatArena
 from sparktorch_b200.runtime.optim import parse_optimizer
 
 
