@@ -37,16 +37,17 @@ class RowBlock:
         from pyspark.sql.types import Row
 
         cols = self.columns
+        # scalar columns are converted to Python values in one vectorised call, vector columns row by row
+        per_col = []
+        for a in self.arrays:
+            if getattr(a, "ndim", 1) >= 2:
+                per_col.append((True, a))
+            elif hasattr(a, "tolist"):
+                per_col.append((False, a.tolist()))
+            else:
+                per_col.append((False, a))
         for i in range(len(self)):
-            vals = []
-            for a in self.arrays:
-                v = a[i]
-                if getattr(v, "ndim", 0) >= 1:
-                    v = DenseVector(v)
-                elif hasattr(v, "item"):
-                    v = v.item()
-                vals.append(v)
-            yield Row._make(cols, vals)
+            yield Row._make(cols, [DenseVector(a[i]) if vec else a[i] for vec, a in per_col])
 
 
 def expand_blocks(it: Iterable) -> Iterator[Any]:

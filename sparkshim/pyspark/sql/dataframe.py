@@ -58,6 +58,20 @@ class DataFrame:
             names = tuple(names[0])
         cs = [_as_column(n) for n in names]
         cols = [c._name for c in cs]
+        srcs = [getattr(c, "_source", None) for c in cs]
+        if all(s is not None and s in self._columns for s in srcs):
+            # plain column references: columnar blocks stay columnar (no per-row objects for dropped columns)
+            def project(_i, it, cols=cols, srcs=srcs):
+                for e in it:
+                    if isinstance(e, RowBlock):
+                        yield RowBlock(cols, [e.column(s) for s in srcs])
+                    else:
+                        yield Row._make(cols, [e[s] for s in srcs])
+
+            project._accepts_blocks = True
+            from pyspark.rdd import PipelinedRDD
+
+            return self._derive(PipelinedRDD(self._rdd, project), cols)
         return self._derive(self._rdd.map(lambda r: Row._make(cols, [c.eval(r) for c in cs])), cols)
 
     def drop(self, *names) -> "DataFrame":

@@ -6,16 +6,17 @@ from typing import Any, Callable
 
 
 class Column:
-    def __init__(self, fn: Callable[[Any], Any], name: str = "col", is_rand: bool = False):
+    def __init__(self, fn: Callable[[Any], Any], name: str = "col", is_rand: bool = False, source: str = None):
         self._fn = fn          # Row -> value
         self._name = name
         self._is_rand = is_rand
+        self._source = source  # set for plain column references: lets select() stay columnar
 
     def eval(self, row):
         return self._fn(row)
 
     def alias(self, name: str) -> "Column":
-        return Column(self._fn, name, self._is_rand)
+        return Column(self._fn, name, self._is_rand, self._source)
 
     def cast(self, dtype) -> "Column":
         conv = dtype.convert if hasattr(dtype, "convert") else (lambda v: v)
@@ -29,7 +30,7 @@ def _as_column(c) -> Column:
 
 
 def col(name: str) -> Column:
-    return Column(lambda r, name=name: r[name], name)
+    return Column(lambda r, name=name: r[name], name, source=name)
 
 
 column = col
