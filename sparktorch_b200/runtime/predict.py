@@ -44,8 +44,12 @@ class BatchPredictor:
         n = X.shape[0]
         outs = []
         pin = self.device.type == "cuda"
-        for s in range(0, n, self.batch_size):
-            xb = torch.from_numpy(np.ascontiguousarray(X[s:s + self.batch_size], dtype=np.float32))
+        # bound one host->device transfer to ~256 MiB: image-sized rows (ResNet: 602 KB each) must not be staged
+        # 65536 at a time
+        row_bytes = max(1, int(np.prod(X.shape[1:])) * 4)
+        step = max(1, min(self.batch_size, (256 << 20) // row_bytes))
+        for s in range(0, n, step):
+            xb = torch.from_numpy(np.ascontiguousarray(X[s:s + step], dtype=np.float32))
             if pin:
                 xb = xb.pin_memory().to(self.device, non_blocking=True)
             out = self.fused(xb) if self.fused is not None else self.model(xb)

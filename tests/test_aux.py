@@ -119,3 +119,26 @@ def test_bench_contract_on_cpu():
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in r["e2e"], k
     assert r["config"]["l2"].startswith("WARNING")          # 1024 rows do not exceed L2 and the line says so
+
+
+def test_batch_predictor_bounds_staging_by_bytes():
+    import numpy as np
+    import torch
+    import torch.nn as nn
+
+    from sparktorch_b200.runtime.predict import BatchPredictor
+
+    calls = []
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(1 << 20, 2)
+
+        def forward(self, x):
+            calls.append(x.shape[0])
+            return self.fc(x)
+
+    bp = BatchPredictor(Net(), torch.device("cpu"), batch_size=65536)
+    out = bp.predict_block(np.zeros((130, 1 << 20), dtype=np.float32))       # 4 MiB rows -> 64 rows per transfer
+    assert out.shape == (130, 2) and calls == [64, 64, 2]
