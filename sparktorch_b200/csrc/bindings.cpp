@@ -382,11 +382,6 @@ class Updater {
   }
   void publish() { check(st::publish_params(a_, cur_stream()), "publish_params"); }
   void set_lr(double lr) { a_.lr = float(lr); }
-  // EXPERIMENTAL: multicast (NVLS) aliases of the param / bf16 arenas -> K-AR publishes with multimem.st
-  void set_multicast_publish(int64_t mc_param_ptr, int64_t mc_wbf16_ptr) {
-    a_.mc_param = reinterpret_cast<float*>(mc_param_ptr);
-    a_.mc_wbf16 = reinterpret_cast<__nv_bfloat16*>(mc_wbf16_ptr);
-  }
 
  private:
   st::UpdateArgs a_;
@@ -611,8 +606,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     int64_t, double, double, double, double, double, double, double, bool, bool, int64_t, bool, int64_t, int64_t>())
       .def("step", &Updater::step)
       .def("publish", &Updater::publish)
-      .def("set_lr", &Updater::set_lr)
-      .def("set_multicast_publish", &Updater::set_multicast_publish);
+      .def("set_lr", &Updater::set_lr);
   m.def("hw_ctrl_words", &hw_ctrl_words);
   m.def("hw_max_stripes", &hw_max_stripes);
   py::class_<HogwildWorker>(m, "HogwildWorker")

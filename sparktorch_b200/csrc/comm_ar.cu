@@ -248,29 +248,13 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
       const int64_t local = e - sg.offset;            // index inside the parameter (may be padding)
       const int64_t count = int64_t(sg.rows) * sg.cols;
       const float pv[4] = {p.x, p.y, p.z, p.w};
-      const bool packed_seg = sg.w_off >= 0 && sg.wt_off < 0 && (sg.cols & 3) == 0 && (sg.w_ld & 3) == 0 &&
-                              (sg.w_off & 3) == 0 && local + 3 < count;
-      // multicast publish: the switch replicates one store to every GPU (incl. this one)
-      const bool mc_pub = MODE == 0 && W > 1 && a.mc_param != nullptr;
-      bool bf16_done = false;
-      if (mc_pub) {
-        if (sg.publish_f32) st_mc_f4(a.mc_param + e, p);
-        else reinterpret_cast<float4*>(a.param[me])[i4] = p;
-        if (packed_seg && a.mc_wbf16 != nullptr) {
-          const int row = int(local / sg.cols), col = int(local % sg.cols);
-          const uint32_t h0 = pack_bf16x2(pv[0], pv[1]), h1 = pack_bf16x2(pv[2], pv[3]);
-          asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(a.mc_wbf16 + sg.w_off + int64_t(row) * sg.w_ld + col),
-                       "f"(__uint_as_float(h0)), "f"(__uint_as_float(h1))
-                       : "memory");
-          bf16_done = true;
-        }
-      }
       for (int k = 0; k < n_pub; ++k) {
         const int peer = (MODE == 0) ? (me + k) % W : me;
-        if (MODE == 0 && !mc_pub && (sg.publish_f32 || peer == me)) reinterpret_cast<float4*>(a.param[peer])[i4] = p;
-        if (!bf16_done && (sg.w_off >= 0 || sg.wt_off >= 0)) {
+        if (MODE == 0 && (sg.publish_f32 || peer == me)) reinterpret_cast<float4*>(a.param[peer])[i4] = p;
+        if (sg.w_off >= 0 || sg.wt_off >= 0) {
           __nv_bfloat16* wb = a.wbf16[peer];
-          const bool packed = packed_seg;
+          const bool packed = sg.w_off >= 0 && sg.wt_off < 0 && (sg.cols & 3) == 0 && (sg.w_ld & 3) == 0 &&
+                              (sg.w_off & 3) == 0 && local + 3 < count;
           if (packed) {   // 4 consecutive columns of one row -> one coalesced 8-byte store
             const int row = int(local / sg.cols), col = int(local % sg.cols);
             uint2 h;

@@ -90,10 +90,6 @@ struct UpdateArgs {
   // one-shot "push" exchange (small arenas): peers have already written their gradients into my receive slots
   float* recv_local;          // [2 parities][world][recv_stride] on THIS gpu (slot [par][me] unused)
   int64_t recv_stride;        // floats per slot (>= numel + tail)
-  // EXPERIMENTAL (SPARKTORCH_MC_PUBLISH=1): publish updated parameters with ONE multimem.st per vector instead of one
-  // store per peer (NVSwitch replicates it): multicast aliases of the param / bf16 arenas, or null
-  float* mc_param;
-  __nv_bfloat16* mc_wbf16;
 };
 constexpr int AR_MAX_BLOCKS = 256;
 constexpr int AR_FLAG_WORDS = 2 * 8 * AR_MAX_BLOCKS;

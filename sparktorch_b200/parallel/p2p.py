@@ -134,12 +134,6 @@ class FusedUpdate:
             self.loss_hist, self.mailbox.data_ptr(), self._segs, self.numel, TAIL, s.kind_id, s.lr, s.beta1, s.beta2,
             s.eps, s.weight_decay, s.momentum, s.dampening, s.nesterov, s.maximize, self.patience, zero_grads,
             self.block.peer_ptrs("recv")[self.rank] if self.exchange == "push" else 0, self.recv_stride)
-        import os
-
-        # EXPERIMENTAL, off by default (not yet validated on hardware): publish through the NVLS multicast mapping
-        if (self.use_multicast and self.exchange != "push" and os.environ.get("SPARKTORCH_MC_PUBLISH", "0") == "1"):
-            self.updater.set_multicast_publish(self.block.multicast_ptr("param"),
-                                               self.block.multicast_ptr("wbf16") if self.wbf16 is not None else 0)
 
     def push_kw(self, mask: int) -> dict:
         """Arguments that make a GEMM mirror its gradient-arena writes into my slot on every peer."""
