@@ -116,24 +116,28 @@ def test_forward_backward_match_autograd(depth):
 
 
 def test_fit_small_resnet_through_engine():
+    """End to end through train_partition: a small bottleneck net memorises 64 random samples (the CPU emulation of the
+    same plan reaches ~0 loss by iteration 12 in fp32 and in bf16 for several seeds, so the margin below is wide)."""
     from sparktorch_b200.runtime.engine import TrainConfig, train_partition
 
     dev = torch.device("cuda:0")
     image, ncls, n = 32, 8, 64
-    model = _small_resnet(ncls, image)
+    torch.manual_seed(0)
+    model = ResNet(ncls, image)
     rng = np.random.default_rng(0)
     X = rng.standard_normal((n, 3 * image * image)).astype(np.float32)
     Y = rng.integers(0, ncls, size=(n, 1)).astype(np.float32)
-    cfg = TrainConfig(iters=30, mini_batch=32, device="cuda", seed=3, engine="fused", sampling="sweep")
-    res = train_partition(0, 1, model, nn.CrossEntropyLoss(), torch.optim.SGD, {"lr": 0.02, "momentum": 0.9}, X, Y, cfg, dev)
+    cfg = TrainConfig(iters=40, mini_batch=32, device="cuda", seed=3, engine="fused", sampling="sweep")
+    res = train_partition(0, 1, model, nn.CrossEntropyLoss(), torch.optim.SGD, {"lr": 0.05, "momentum": 0.9}, X, Y, cfg, dev)
     h = res.history
     assert h["engine"] == "fused_resnet", h["engine"]
     tl = h["train_loss"]
-    assert len(tl) == 30 and all(np.isfinite(tl))
-    assert np.mean(tl[-6:]) < np.mean(tl[:6]), tl            # memorises 64 random samples (two alternating batches)
+    assert len(tl) == 40 and all(np.isfinite(tl))
+    assert np.mean(tl[-6:]) < 0.3 * np.mean(tl[:4]), tl
     sd = res.state_dict
-    assert sd["stem.1.num_batches_tracked"].item() == 30
-    m2 = _small_resnet(ncls, image)
+    assert sd["stem.1.num_batches_tracked"].item() == 40
+    torch.manual_seed(0)
+    m2 = ResNet(ncls, image)
     m2.load_state_dict(sd)
 
 
