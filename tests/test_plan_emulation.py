@@ -334,3 +334,142 @@ def test_mnist_cnn_plan_with_counter_based_dropout2d():
         plan.update()
         ref_opt.step()
     assert 0.5 < sum(kept) / len(kept) < 0.95 and len(set(kept)) > 1        # masks vary per iteration, ~75 % kept
+
+
+def test_mlp_plan_randomised_architectures_and_optimizers():
+    """30 random MLPs (ragged widths, optional biases / ReLUs, CE or MSE, SGD / Adam / AdamW variants, with and without
+    batch windows) - the plan must track autograd + torch.optim step by step."""
+    import random
+
+    rnd = random.Random(1234)
+    for case in range(30):
+        torch.manual_seed(100 + case)
+        depth = rnd.randint(1, 4)
+        dims = [rnd.choice([3, 8, 10, 17, 24, 33])] + [rnd.choice([5, 8, 12, 20, 31]) for _ in range(depth - 1)]
+        kind = rnd.choice(["ce", "mse"])
+        out_dim = rnd.choice([2, 5, 10, 32, 40]) if kind == "ce" else rnd.choice([1, 3, 8])
+        dims.append(out_dim)
+        layers = []
+        for i in range(depth):
+            layers.append(nn.Linear(dims[i], dims[i + 1], bias=rnd.random() < 0.8))
+            if i < depth - 1 and rnd.random() < 0.8:
+                layers.append(nn.ReLU())
+        model = nn.Sequential(*layers)
+        ref = copy.deepcopy(model)
+        opt = rnd.choice(["sgd", "sgd_m", "sgd_nest", "adam", "adam_wd", "adamw"])
+        if opt == "sgd":
+            cls, kw = torch.optim.SGD, {"lr": 0.05, "weight_decay": rnd.choice([0.0, 1e-3])}
+        elif opt == "sgd_m":
+            cls, kw = torch.optim.SGD, {"lr": 0.03, "momentum": 0.9, "dampening": rnd.choice([0.0, 0.1])}
+        elif opt == "sgd_nest":
+            cls, kw = torch.optim.SGD, {"lr": 0.03, "momentum": 0.8, "nesterov": True}
+        elif opt == "adam":
+            cls, kw = torch.optim.Adam, {"lr": 3e-3, "betas": (0.8, 0.95)}
+        elif opt == "adam_wd":
+            cls, kw = torch.optim.Adam, {"lr": 3e-3, "weight_decay": 1e-2}
+        else:
+            cls, kw = torch.optim.AdamW, {"lr": 3e-3, "weight_decay": 5e-2}
+        spec = parse_optimizer(cls, kw)
+        low = lower_mlp(model)
+        assert low is not None, case
+        crit = nn.CrossEntropyLoss() if kind == "ce" else nn.MSELoss()
+        B = rnd.choice([4, 9, 16])
+        windowed = rnd.random() < 0.5
+        plan = _emulated(FusedMLP, model, low, loss_kind(crit, low), spec, B)
+        plan.fu.updater.publish()
+        windowed = windowed and plan.fuse_loss              # windows need the loss fused in the last GEMM
+        g = torch.Generator().manual_seed(500 + case)
+        n_win = 3
+        X = torch.randn(B * n_win, dims[0], generator=g)
+        Y = torch.randint(0, out_dim, (B * n_win,), generator=g) if kind == "ce" else torch.randn(B * n_win, out_dim, generator=g)
+        batches = [(X[(i % n_win) * B: (i % n_win + 1) * B], Y[(i % n_win) * B: (i % n_win + 1) * B]) for i in range(4)]
+        if windowed:
+            plan.train["acts"][0] = X.clone()
+            plan.train["tgt"] = Y.to(torch.int32) if kind == "ce" else Y.clone()
+            plan.window = (n_win, B)
+        try:
+            _compare_steps(plan, model, ref, cls(ref.parameters(), **kw), crit, batches, windowed=windowed)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: dims {dims} kind {kind} opt {opt} {kw} B {B} windowed {windowed}: {e}") from None
+
+
+class _RandCNN(nn.Module):
+    def __init__(self, in_shape, conv_specs, head):
+        super().__init__()
+        self.in_shape = in_shape
+        c = in_shape[0]
+        self.convs = nn.ModuleList()
+        self.meta = []
+        for (cout, k, s, p, relu, pool) in conv_specs:
+            self.convs.append(nn.Conv2d(c, cout, k, stride=s, padding=p, bias=True))
+            self.meta.append((relu, pool))
+            c = cout
+        self.head = nn.ModuleList([nn.Linear(a, b) for a, b in head])
+
+    def forward(self, x):
+        x = x.view(-1, self.in_shape[0], self.in_shape[1], self.in_shape[2])
+        for conv, (relu, pool) in zip(self.convs, self.meta):
+            x = conv(x)
+            if relu:
+                x = torch.relu(x)
+            if pool:
+                x = nn.functional.max_pool2d(x, pool)
+        x = torch.flatten(x, 1)
+        for i, lin in enumerate(self.head):
+            x = lin(x)
+            if i < len(self.head) - 1:
+                x = torch.relu(x)
+        return x
+
+
+def test_cnn_plan_randomised_geometries():
+    import random
+
+    rnd = random.Random(99)
+    done = 0
+    for case in range(40):
+        C0, H0 = rnd.choice([1, 3]), rnd.choice([10, 12, 14])
+        n_conv = rnd.randint(1, 3)
+        specs, c, h = [], C0, H0
+        ok = True
+        for i in range(n_conv):
+            k = rnd.choice([3, 5])
+            s = rnd.choice([1, 2]) if i == 0 else 1
+            p = rnd.choice([0, 1, 2])
+            cout = rnd.choice([4, 8, 12])
+            pool = rnd.choice([0, 2])
+            oh = (h + 2 * p - k) // s + 1
+            if oh < 2:
+                ok = False
+                break
+            if pool:
+                oh //= pool
+            if oh < 1:
+                ok = False
+                break
+            specs.append((cout, k, s, p, rnd.random() < 0.8, pool))
+            c, h = cout, oh
+        if not ok:
+            continue
+        feat = c * h * h
+        ncls = rnd.choice([3, 6, 10])
+        head = [(feat, ncls)] if rnd.random() < 0.5 else [(feat, 16), (16, ncls)]
+        torch.manual_seed(300 + case)
+        model = _RandCNN((C0, H0, H0), specs, head)
+        low = lower_cnn(model, C0 * H0 * H0)
+        if low is None:
+            continue
+        ref = copy.deepcopy(model)
+        kw = {"lr": 3e-3}
+        spec = parse_optimizer(torch.optim.Adam, kw)
+        B = rnd.choice([3, 6])
+        plan = _emulated(FusedCNN, model, low, "ce", spec, B)
+        plan.fu.updater.publish()
+        g = torch.Generator().manual_seed(700 + case)
+        batches = [(torch.randn(B, C0 * H0 * H0, generator=g), torch.randint(0, ncls, (B,), generator=g)) for _ in range(2)]
+        try:
+            _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: in {(C0, H0)} convs {specs} head {head} B {B}: {e}") from None
+        done += 1
+    assert done >= 15, done
