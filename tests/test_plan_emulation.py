@@ -473,3 +473,49 @@ def test_cnn_plan_randomised_geometries():
             raise AssertionError(f"case {case}: in {(C0, H0)} convs {specs} head {head} B {B}: {e}") from None
         done += 1
     assert done >= 15, done
+
+
+@pytest.mark.parametrize("which", ["mlp", "cnn", "resnet"])
+def test_validation_forward_fills_the_shared_loss_slot_and_leaves_gradients_alone(which):
+    """With validationPct the step is train fwd (loss -> tail[2]) + bwd + validation fwd (loss -> tail[0], the slot that
+    rides in the all-reduce and drives early stopping) + update."""
+    torch.manual_seed(8)
+    spec = parse_optimizer(torch.optim.Adam, {"lr": 1e-3})
+    B, NV = 6, 10
+    if which == "mlp":
+        model = nn.Sequential(nn.Linear(12, 16), nn.ReLU(), nn.Linear(16, 4))
+        low, d0, ncls = lower_mlp(model), 12, 4
+        plan = FusedMLP(model, low, "ce", spec, 1, 0, torch.device("cpu"), B, NV, 0, 8,
+                        backend_factory=lambda n, w: EmulatedUpdate(n, spec, w), ops=reference, act_dtype=torch.float32)
+    elif which == "cnn":
+        model = _ConvNet()
+        low, d0, ncls = lower_cnn(model, 144), 144, 6
+        plan = FusedCNN(model, low, "ce", spec, 1, 0, torch.device("cpu"), B, NV, 0, 8,
+                        backend_factory=lambda n, w: EmulatedUpdate(n, spec, w), ops=reference, act_dtype=torch.float32)
+    else:
+        model = ResNet(8, 32)
+        low, d0, ncls = lower_resnet(model, 3 * 32 * 32), 3 * 32 * 32, 8
+        plan = FusedResNet(model, low, "ce", spec, 1, 0, torch.device("cpu"), B, NV, 0, 8,
+                           backend_factory=lambda n, w: EmulatedUpdate(n, spec, w), ops=reference, act_dtype=torch.float32)
+    ref = copy.deepcopy(model)
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(12)
+    x, y = torch.randn(B, d0, generator=g), torch.randint(0, ncls, (B,), generator=g)
+    xv, yv = torch.randn(NV, d0, generator=g), torch.randint(0, ncls, (NV,), generator=g)
+    plan.train["acts"][0].copy_(x)
+    plan.train["tgt"].copy_(y.to(torch.int32))
+    plan.val["acts"][0].copy_(xv)
+    plan.val["tgt"].copy_(yv.to(torch.int32))
+    plan.forward(plan.train, slot=plan.train_loss_slot, train=True)
+    plan.backward(plan.train)
+    grads = plan.fu.grad[: plan.fu.numel].clone()
+    bn_before = {n: b.clone() for n, b in model.named_buffers()}
+    plan.forward(plan.val, slot=plan.loss_slot, train=False)
+    torch.testing.assert_close(plan.fu.grad[: plan.fu.numel], grads, rtol=0, atol=0)        # validation adds no gradient
+    for n, b in model.named_buffers():
+        torch.testing.assert_close(b, bn_before[n], rtol=0, atol=0)                           # ... and no BN statistics
+    loss_train = nn.functional.cross_entropy(ref(x), y)
+    with torch.no_grad():
+        loss_val = nn.functional.cross_entropy(ref(xv), yv)      # train-mode BN on the validation batch, like the plan
+    assert abs(float(plan.train_loss_slot[0]) - float(loss_train.detach())) < 1e-4
+    assert abs(float(plan.loss_slot[0]) - float(loss_val)) < 1e-4
