@@ -1,5 +1,7 @@
 """End-to-end checks of the fused B200 path against the eager fp32 engine
 (``pytest -m gpu`` on the GPU box)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -319,3 +321,27 @@ def test_fused_cnn_predictor_matches_eager():
     assert out.shape == want.shape
     np.testing.assert_allclose(out, want, rtol=5e-2, atol=5e-2)
     assert (out.argmax(1) == want.argmax(1)).mean() > 0.97
+
+
+@pytest.mark.skipif(os.environ.get("SPARKTORCH_PENDING_TESTS", "0") != "1",
+                    reason="written after the GPU budget of round 1 was spent - enable with SPARKTORCH_PENDING_TESTS=1 and promote once green")
+def test_hogwild_fused_cnn_worker_matches_sync_fused_on_one_gpu():
+    """Same as the MLP variant, for the CNN plan: conv weights gathered through K-AG, split head, 'sweep' windows."""
+    import copy
+
+    from sparktorch_b200.models import MnistCNN
+    from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
+    from sparktorch_b200.runtime.engine import TrainConfig
+
+    X, Y = _data(n=1024)
+    torch.manual_seed(2)
+    net = MnistCNN(p_drop=0.0)
+    dev = torch.device("cuda", 0)
+    cfg = TrainConfig(iters=24, mini_batch=128, device="cuda", seed=4, sampling="sweep")
+    hw = train_partition_hogwild_fused(0, 1, copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3},
+                                       X, Y, cfg, dev, window_len=1)
+    assert hw is not None and hw.history["comm"] == "HogwildP2P+K-AG" and hw.history["iters_run"] == 24
+    ref = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=128, engine="fused",
+               sampling="sweep", seed=4)
+    np.testing.assert_allclose(hw.history["train_loss"], ref.history["train_loss"], rtol=2e-2, atol=5e-3)
+    assert np.mean(ref.history["train_loss"][-4:]) < np.mean(ref.history["train_loss"][:4])      # labels of the right window
