@@ -255,7 +255,8 @@ def train_partition(
             if res is not None:
                 return res
             if cfg.engine == "fused":
-                raise RuntimeError("engine='fused' requested but the model/criterion/optimizer is not lowerable")
+                raise RuntimeError("engine='fused' requested but the model/criterion/optimizer is not lowerable "
+                                   "(or checkpointing/resume was requested, which only the eager engine implements)")
         except ImportError:
             if cfg.engine == "fused":
                 raise

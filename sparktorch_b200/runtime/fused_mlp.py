@@ -370,6 +370,10 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
 
     if cfg.precision not in ("auto", "bf16") or not native.available():
         return None
+    if cfg.checkpoint_dir and (cfg.checkpoint_every > 0 or cfg.resume):
+        # mid-training checkpoints / resume are implemented by the eager engine (same K-AR update kernel, its optimizer
+        # shard and step state are exported); the graph-replay loop has no checkpoint hook yet
+        return None
     spec = parse_optimizer(opt_cls, opt_params)
     if spec.kind == "other" or world > 8:
         return None
