@@ -370,6 +370,8 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
 
     if cfg.precision not in ("auto", "bf16") or not native.available():
         return None
+    if getattr(cfg, "comm", "auto") not in ("auto", "p2p"):
+        return None                     # an explicit collective (NCCL/gloo oracle) exchange was requested
     if cfg.checkpoint_dir and (cfg.checkpoint_every > 0 or cfg.resume):
         # mid-training checkpoints / resume are implemented by the eager engine (same K-AR update kernel, its optimizer
         # shard and step state are exported); the graph-replay loop has no checkpoint hook yet
