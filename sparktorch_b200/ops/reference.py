@@ -31,13 +31,17 @@ def _window_offset(win_state, window_rows, n_windows) -> int:
 def gemm_bf16(A, a_mn, B, b_mn, M, N, K, alpha: float = 1.0, bias=None, relu: bool = False, mask_src=None, out_bf16=None,
               out_t_bf16=None, out_f32=None, out_t_f32=None, atomic_f32: bool = False, colsum=None, block_n: int = 0,
               split_k: int = 1, loss_kind: int = 0, labels=None, target=None, loss_slot=None, loss_scale: float = 1.0,
-              win_state=None, window_rows: int = 0, n_windows: int = 0, win_flags: int = 0, colsumsq=None, **unsupported):
+              win_state=None, window_rows: int = 0, n_windows: int = 0, win_flags: int = 0, colsumsq=None, peer_table=None,
+              peer_shard_elems: int = 0, peer_w_off: int = 0, peer_bias_off: int = -1, peer_fill_local: bool = False, **unsupported):
     """D[M, N] = A · Bᵀ with the epilogue options the plans use (A stored [M,K], or [K,M] when ``a_mn``; same for B).
 
     ``win_flags``: 1 - A is the resident partition, the batch is the window of the current iteration; 2 - same for the
     reduction rows of an MN-major B; 4 - labels / targets are taken from the same window.
     ``loss_kind`` 1 (softmax-CE, mean over rows) / 2 (MSE, mean over M*N): the accumulator becomes dLoss/dOutput, so
-    ``out_bf16`` / ``colsum`` emit dZ / db while ``out_f32`` keeps the raw output."""
+    ``out_bf16`` / ``colsum`` emit dZ / db while ``out_f32`` keeps the raw output.
+    ``peer_table`` (K-AG, here a list of per-owner fp32 arenas): B[n, k] and the bias are gathered from the owner of flat
+    element ``f = peer_w_off + n*K + k`` (owner = f // peer_shard_elems); ``peer_fill_local`` leaves the gathered
+    weights in ``B`` for the dgrad GEMM."""
     for k, v in unsupported.items():
         if v not in (None, 0, False, 0.0, 1.0):
             raise NotImplementedError(f"reference gemm_bf16: option {k} is not emulated")
@@ -46,7 +50,19 @@ def gemm_bf16(A, a_mn, B, b_mn, M, N, K, alpha: float = 1.0, bias=None, relu: bo
     b_off = off if (win_flags & 2) else 0
     l_off = off if (win_flags & 4) else 0
     Am = _f(A[:K, :M]).t() if a_mn else _f(A[a_off: a_off + M, :K])
-    Bm = _f(B[b_off: b_off + K, :N]).t() if b_mn else _f(B[:N, :K])
+    if peer_table is not None:
+        assert not b_mn
+        f = peer_w_off + torch.arange(N * K)
+        owner = f // peer_shard_elems
+        flat = torch.stack([_f(t_) for t_ in peer_table])            # [owners, numel]
+        Bm = flat[owner, f].reshape(N, K)
+        if peer_fill_local:
+            B[:N, :K] = Bm.to(B.dtype)
+        if peer_bias_off >= 0:
+            fb = peer_bias_off + torch.arange(N)
+            bias = flat[fb // peer_shard_elems, fb]
+    else:
+        Bm = _f(B[b_off: b_off + K, :N]).t() if b_mn else _f(B[:N, :K])
     D = (Am @ Bm.t()) * alpha
     if bias is not None:
         D = D + _f(bias[:N])

@@ -69,3 +69,48 @@ class EmulatedUpdate:
 
     def last_loss(self) -> float:
         return float(self.loss_hist[max(0, self.steps - 1)])
+
+
+class EmulatedHogwild(EmulatedUpdate):
+    """Single-process stand-in for ``parallel.hogwild_p2p.HogwildBackend``: W notional owners, each holding an arena in
+    which only its own shard is authoritative (the rest is poisoned with NaN, so a gather from the wrong owner is
+    caught); the forward GEMMs gather weights through ``peer_table`` (K-AG), ``step`` applies the update to the owners'
+    shards (the remote-apply push with one worker)."""
+
+    def __init__(self, numel: int, spec: OptSpec, wbf16_elems: int, world: int = 3, max_iters: int = 64):
+        super().__init__(numel, spec, wbf16_elems, max_iters)
+        self.world = world
+        n4 = numel // 4
+        self.shard_elems = ((n4 + world - 1) // world) * 4
+        self.peer_table = [torch.full((numel,), float("nan")) for _ in range(world)]
+        self.updater = _EmulatedHogwildWorker(self)
+
+    def scatter(self) -> None:
+        """owners <- the local snapshot (initial weights)"""
+        for r, t in enumerate(self.peer_table):
+            lo, hi = r * self.shard_elems, min(self.numel, (r + 1) * self.shard_elems)
+            if lo < hi:
+                t[lo:hi] = self.param[lo:hi]
+
+    def gather(self) -> None:
+        """local snapshot <- owners (the final pull)"""
+        for r, t in enumerate(self.peer_table):
+            lo, hi = r * self.shard_elems, min(self.numel, (r + 1) * self.shard_elems)
+            if lo < hi:
+                self.param[lo:hi] = t[lo:hi]
+
+
+class _EmulatedHogwildWorker(_EmulatedUpdater):
+    def publish(self) -> None:          # weights are gathered inside the forward GEMMs, nothing to build up front
+        self.o.scatter()
+
+    def step(self) -> None:
+        o = self.o
+        o.gather()
+        o.steps += 1
+        apply_update_(o.spec, o.param, o.grad[: o.numel], o.opt_state, o.steps)
+        o.loss_hist[o.steps - 1] = o.grad[o.numel]
+        o.mailbox[1] = o.steps
+        o.state[4] = o.steps
+        o.grad.zero_()
+        o.scatter()

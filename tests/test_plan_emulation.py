@@ -519,3 +519,30 @@ def test_validation_forward_fills_the_shared_loss_slot_and_leaves_gradients_alon
         loss_val = nn.functional.cross_entropy(ref(xv), yv)      # train-mode BN on the validation batch, like the plan
     assert abs(float(plan.train_loss_slot[0]) - float(loss_train.detach())) < 1e-4
     assert abs(float(plan.loss_slot[0]) - float(loss_val)) < 1e-4
+
+
+@pytest.mark.parametrize("which", ["mlp", "cnn"])
+def test_k_ag_forward_gathers_weights_from_their_owners(which):
+    """Hogwild layout: parameters sharded over W owners (every other copy poisoned with NaN); the forward GEMMs of the
+    plan gather weights AND biases through peer_table, the dgrad GEMMs use the gathered local copy."""
+    from sparktorch_b200.runtime.emulation import EmulatedHogwild
+
+    torch.manual_seed(9)
+    kw = {"lr": 2e-3}
+    spec = parse_optimizer(torch.optim.Adam, kw)
+    B = 5
+    if which == "mlp":
+        model = nn.Sequential(nn.Linear(12, 20), nn.ReLU(), nn.Linear(20, 16), nn.ReLU(), nn.Linear(16, 4))
+        low, d0, ncls, cls = lower_mlp(model), 12, 4, FusedMLP
+    else:
+        model = _ConvNet()
+        low, d0, ncls, cls = lower_cnn(model, 144), 144, 6, FusedCNN
+    ref = copy.deepcopy(model)
+    plan = cls(model, low, "ce", spec, 1, 0, torch.device("cpu"), B, 0, 0, 16,
+               backend_factory=lambda n, w: EmulatedHogwild(n, spec, w, world=3), ops=reference, act_dtype=torch.float32)
+    assert all(plan.peer_kw[k] for k in (plan.peer_kw if isinstance(plan.peer_kw, dict) else range(len(plan.peer_kw))))
+    plan.fu.updater.publish()
+    g = torch.Generator().manual_seed(13)
+    batches = [(torch.randn(B, d0, generator=g), torch.randint(0, ncls, (B,), generator=g)) for _ in range(3)]
+    _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
+    assert not torch.isnan(plan.fu.param).any()
