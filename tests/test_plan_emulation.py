@@ -244,10 +244,13 @@ def test_mnist_cnn_plan_without_dropout_matches_autograd():
     _compare_steps(plan, model, ref, torch.optim.Adam(ref.parameters(), **kw), nn.CrossEntropyLoss(), batches)
 
 
-def test_cnn_plan_split_head_reads_labels_of_the_current_window():
+@pytest.mark.parametrize("backend", ["sync", "hogwild"])
+def test_cnn_plan_split_head_reads_labels_of_the_current_window(backend):
     """MnistCNN's 3872-wide head takes the split-K + stand-alone loss path; with 'sweep' windows the loss kernel must read
-    the labels of the SAME window the im2col reads the images from."""
+    the labels of the SAME window the im2col reads the images from (both for the synchronous plan and for the hogwild
+    worker, whose forward GEMMs additionally gather the weights from their owners)."""
     from sparktorch_b200.models import MnistCNN
+    from sparktorch_b200.runtime.emulation import EmulatedHogwild
 
     torch.manual_seed(5)
     model = MnistCNN(p_drop=0.0)
@@ -256,7 +259,11 @@ def test_cnn_plan_split_head_reads_labels_of_the_current_window():
     spec = parse_optimizer(torch.optim.Adam, kw)
     low = lower_cnn(model, 784)
     B, windows = 4, 3
-    plan = _emulated(FusedCNN, model, low, "ce", spec, B)
+    if backend == "sync":
+        plan = _emulated(FusedCNN, model, low, "ce", spec, B)
+    else:
+        plan = FusedCNN(model, low, "ce", spec, 1, 0, torch.device("cpu"), B, 0, 0, 16,
+                        backend_factory=lambda n, w: EmulatedHogwild(n, spec, w, world=2), ops=reference, act_dtype=torch.float32)
     assert plan._deep_head(B)
     plan.fu.updater.publish()
     g = torch.Generator().manual_seed(8)
