@@ -4,9 +4,11 @@ from setuptools import find_packages, setup
 
 setup(
     name="sparktorch-b200",
-    version="0.1.0",
+    version="0.2.0",
     description="Blackwell-native distributed training/inference of PyTorch networks with the SparkTorch API",
-    packages=find_packages(include=["sparktorch", "sparktorch.*", "sparktorch_b200", "sparktorch_b200.*"]),
+    # sparkshim = the single-node PySpark-compatible runtime used when no real pyspark is importable
+    # (sparktorch_b200/_spark.py appends <site-packages>/sparkshim to sys.path in that case)
+    packages=find_packages(include=["sparktorch", "sparktorch.*", "sparktorch_b200", "sparktorch_b200.*", "sparkshim", "sparkshim.*"]),
     package_data={"sparktorch_b200": ["_C*.so", "csrc/*.cu", "csrc/*.cuh", "csrc/*.h", "csrc/*.cpp"]},
     install_requires=["torch", "dill", "numpy", "cloudpickle"],
     extras_require={"spark": ["pyspark>=3.2"]},

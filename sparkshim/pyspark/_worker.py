@@ -9,6 +9,9 @@ import cloudpickle
 
 
 def serve(host: str, port: int, slot: int) -> None:
+    import os
+
+    os.environ["SPARKSHIM_EXECUTOR"] = "1"      # a dedicated worker process (stall watchdogs may terminate it, never the driver)
     from pyspark._cluster import _AUTH, bind_gpu
     from pyspark.taskcontext import BarrierTaskContext, TaskContext, _set_context
 

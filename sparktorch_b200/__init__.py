@@ -1,17 +1,40 @@
 """sparktorch_b200 – a Blackwell-native re-implementation of SparkTorch's
 capabilities (Spark ML Estimator/Transformer for distributed PyTorch training
 and inference) – see DESIGN.md.  Public names match the reference package
-(sparktorch/__init__.py:1-4)."""
-__version__ = "0.1.0"
+(sparktorch/__init__.py:1-4).
 
-from sparktorch_b200._spark import ensure_pyspark
+The public names are resolved lazily (PEP 562): importing a sub-module such as
+``sparktorch_b200.csrc.build`` or ``sparktorch_b200.ops.native`` does not pull in
+the Spark layer, so the extension can be built and the kernels used on a box
+without any Spark API on ``sys.path``."""
+import importlib
 
-ensure_pyspark()
+__version__ = "0.2.0"
 
-from sparktorch_b200.util import serialize_torch_obj, serialize_torch_obj_lazy  # noqa: E402
-from sparktorch_b200.torch_distributed import SparkTorch, SparkTorchModel  # noqa: E402
-from sparktorch_b200.pipeline_util import PysparkPipelineWrapper  # noqa: E402
-from sparktorch_b200.inference import attach_pytorch_model_to_pipeline, create_spark_torch_model  # noqa: E402
-
+_LAZY = {
+    "serialize_torch_obj": "sparktorch_b200.util",
+    "serialize_torch_obj_lazy": "sparktorch_b200.util",
+    "SparkTorch": "sparktorch_b200.torch_distributed",
+    "SparkTorchModel": "sparktorch_b200.torch_distributed",
+    "PysparkPipelineWrapper": "sparktorch_b200.pipeline_util",
+    "attach_pytorch_model_to_pipeline": "sparktorch_b200.inference",
+    "create_spark_torch_model": "sparktorch_b200.inference",
+}
 __all__ = ["serialize_torch_obj", "serialize_torch_obj_lazy", "SparkTorch", "SparkTorchModel",
            "PysparkPipelineWrapper", "create_spark_torch_model", "attach_pytorch_model_to_pipeline"]
+
+
+def __getattr__(name):
+    target = _LAZY.get(name)
+    if target is None:
+        raise AttributeError(f"module 'sparktorch_b200' has no attribute {name!r}")
+    from sparktorch_b200._spark import ensure_pyspark
+
+    ensure_pyspark()
+    value = getattr(importlib.import_module(target), name)
+    globals()[name] = value
+    return value
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_LAZY))

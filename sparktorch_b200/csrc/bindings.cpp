@@ -10,6 +10,7 @@
 
 #include "gemm_sm100.h"
 #include "kernels.h"
+#include "mlp_step.h"
 
 namespace {
 
@@ -444,6 +445,102 @@ class HogwildWorker {
 int64_t hw_ctrl_words() { return st::HW_CTRL_WORDS; }
 int64_t hw_max_stripes() { return st::HW_MAX_STRIPES; }
 
+
+// ------------------------------------------------------------------ K-STEP: whole training steps in one persistent kernel
+// (csrc/mlp_step.cu).  The task graph, tensor-map table and peer pointer table are built by runtime/mega_mlp.py.
+py::bytes make_tmap_bytes(int64_t ptr, int64_t rows, int64_t cols, int64_t ld, int64_t box_rows) {
+  CUtensorMap map;
+  check(st::make_tmap_bf16_2d(&map, reinterpret_cast<const void*>(ptr), uint64_t(rows), uint64_t(cols), uint64_t(ld), uint32_t(box_rows)),
+        "cuTensorMapEncodeTiled");
+  return py::bytes(reinterpret_cast<const char*>(&map), sizeof(map));
+}
+
+class MlpStep {
+ public:
+  MlpStep(const Tensor& tasks, const Tensor& n_tasks, const Tensor& tmaps, const Tensor& peers, const Tensor& counters,
+          int64_t flags_local_ptr, int64_t world, int64_t rank, int64_t grad_ptr, int64_t param_ptr, int64_t wbf16_ptr,
+          int64_t mc_grad_ptr, int64_t mc_param_ptr, int64_t mc_wbf16_ptr, const OptT& m, const OptT& v, int64_t shard_lo,
+          const Tensor& segs, const Tensor& state, const OptT& loss_hist, int64_t mailbox_ptr, int64_t kind, double lr, double beta1,
+          double beta2, double eps, double weight_decay, double momentum, double dampening, bool nesterov, bool maximize,
+          int64_t patience, int64_t decide_cnt, int64_t n_mt, int64_t loss_off, int64_t window_rows, int64_t n_windows,
+          const Tensor& error)
+      : tasks_(tasks), n_tasks_(n_tasks), tmaps_(tmaps), peers_(peers), counters_(counters), segs_(segs), state_(state),
+        error_(error), m_(m), v_(v), loss_hist_(loss_hist) {
+    TORCH_CHECK(tasks.is_cuda() && n_tasks.is_cuda() && tmaps.is_cuda() && peers.is_cuda() && counters.is_cuda() && segs.is_cuda() && error.is_cuda());
+    TORCH_CHECK(n_tasks.scalar_type() == at::kInt && counters.scalar_type() == at::kInt && error.scalar_type() == at::kInt && error.numel() >= 4);
+    grid_ = int(n_tasks.numel());
+    TORCH_CHECK(int64_t(tasks.numel() * tasks.element_size()) == int64_t(grid_) * st::MS_MAX_TASKS * int64_t(sizeof(st::MsTask)), "task table size");
+    TORCH_CHECK(int64_t(peers.numel() * peers.element_size()) == int64_t(sizeof(st::MsPeerTable)), "peer table size");
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(tmaps.data_ptr()) & 63) == 0 && (reinterpret_cast<uintptr_t>(tasks.data_ptr()) & 15) == 0);
+    p_ = st::MsParams{};
+    p_.tasks = reinterpret_cast<const st::MsTask*>(tasks.data_ptr());
+    p_.n_tasks = n_tasks.data_ptr<int32_t>();
+    p_.tmaps = reinterpret_cast<const CUtensorMap*>(tmaps.data_ptr());
+    p_.peers = reinterpret_cast<const st::MsPeerTable*>(peers.data_ptr());
+    p_.counters = reinterpret_cast<uint32_t*>(counters.data_ptr<int32_t>());
+    p_.flags_local = reinterpret_cast<uint32_t*>(flags_local_ptr);
+    p_.world = int(world); p_.rank = int(rank);
+    p_.grad_local = reinterpret_cast<float*>(grad_ptr);
+    p_.param_local = reinterpret_cast<float*>(param_ptr);
+    p_.wbf16_local = reinterpret_cast<__nv_bfloat16*>(wbf16_ptr);
+    p_.mc_grad = reinterpret_cast<float*>(mc_grad_ptr);
+    p_.mc_param = reinterpret_cast<float*>(mc_param_ptr);
+    p_.mc_wbf16 = reinterpret_cast<__nv_bfloat16*>(mc_wbf16_ptr);
+    p_.m = m ? m->data_ptr<float>() : nullptr;
+    p_.v = v ? v->data_ptr<float>() : nullptr;
+    p_.shard_lo = shard_lo;
+    p_.segs = reinterpret_cast<const st::ParamSegment*>(segs.data_ptr());
+    TORCH_CHECK(state.numel() * state.element_size() >= int64_t(sizeof(st::StepState)));
+    p_.state = reinterpret_cast<st::StepState*>(state.data_ptr());
+    p_.loss_hist = loss_hist ? loss_hist->data_ptr<float>() : nullptr;
+    p_.max_iters = loss_hist ? loss_hist->numel() : 0;
+    p_.mailbox = reinterpret_cast<volatile uint32_t*>(mailbox_ptr);
+    p_.kind = int(kind); p_.lr = float(lr); p_.beta1 = float(beta1); p_.beta2 = float(beta2); p_.eps = float(eps);
+    p_.weight_decay = float(weight_decay); p_.momentum = float(momentum); p_.dampening = float(dampening);
+    p_.nesterov = nesterov; p_.maximize = maximize; p_.patience = int(patience); p_.decide_cnt = int(decide_cnt);
+    p_.n_mt = int(n_mt); p_.loss_off = loss_off; p_.window_rows = window_rows; p_.n_windows = n_windows > 0 ? n_windows : 1;
+    p_.error = reinterpret_cast<uint32_t*>(error.data_ptr<int32_t>());
+  }
+  void set_prof(const OptT& prof) {
+    prof_ = prof;
+    if (prof) {
+      TORCH_CHECK(prof->is_cuda() && prof->scalar_type() == at::kLong && prof->numel() >= int64_t(grid_) * st::MS_MAX_TASKS * 8);
+      p_.prof = reinterpret_cast<long long*>(prof->data_ptr());
+    } else {
+      p_.prof = nullptr;
+    }
+  }
+  // n_steps whole training steps in one launch on the current stream
+  void run(int64_t iter0, int64_t step0, int64_t epoch0, int64_t n_steps) {
+    p_.iter0 = iter0; p_.step0 = step0; p_.epoch0 = uint32_t(epoch0); p_.n_steps = int(n_steps);
+    check(st::mlp_step_launch(p_, grid_, cur_stream()), "mlp_step_launch");
+  }
+  // `iters` steps, `per_launch` steps per kernel; returns the steps launched (stops early once the device latched a stop)
+  int64_t run_many(int64_t iter0, int64_t step0, int64_t epoch0, int64_t iters, int64_t per_launch, int64_t mailbox_ptr) {
+    volatile uint32_t* mb = reinterpret_cast<volatile uint32_t*>(mailbox_ptr);
+    int64_t done = 0;
+    if (per_launch < 1) per_launch = 1;
+    while (done < iters) {
+      const int64_t n = std::min(per_launch, iters - done);
+      run(iter0 + done, step0 + done, epoch0 + done, n);
+      done += n;
+      if (mb != nullptr && mb[0] != 0) break;
+    }
+    return done;
+  }
+  int64_t grid() const { return grid_; }
+
+ private:
+  st::MsParams p_;
+  int grid_ = 0;
+  Tensor tasks_, n_tasks_, tmaps_, peers_, counters_, segs_, state_, error_;
+  OptT m_, v_, loss_hist_, prof_;
+};
+int64_t ms_task_bytes() { return int64_t(sizeof(st::MsTask)); }
+int64_t ms_max_tasks() { return st::MS_MAX_TASKS; }
+int64_t ms_max_flags() { return st::MS_MAX_FLAGS; }
+int64_t ms_smem_bytes() { return st::ms_smem_bytes(); }
+
 py::bytes pack_segments(const std::vector<std::vector<int64_t>>& rows) {
   std::vector<st::ParamSegment> segs(rows.size());
   for (size_t i = 0; i < rows.size(); ++i) {
@@ -618,6 +715,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("push", &HogwildWorker::push)
       .def("step", &HogwildWorker::step)
       .def("warm", &HogwildWorker::warm);
+  m.def("make_tmap_bytes", &make_tmap_bytes);
+  m.def("ms_task_bytes", &ms_task_bytes);
+  m.def("ms_max_tasks", &ms_max_tasks);
+  m.def("ms_max_flags", &ms_max_flags);
+  m.def("ms_smem_bytes", &ms_smem_bytes);
+  py::class_<MlpStep>(m, "MlpStep")
+      .def(py::init<const Tensor&, const Tensor&, const Tensor&, const Tensor&, const Tensor&, int64_t, int64_t, int64_t, int64_t,
+                    int64_t, int64_t, int64_t, int64_t, int64_t, const OptT&, const OptT&, int64_t, const Tensor&, const Tensor&,
+                    const OptT&, int64_t, int64_t, double, double, double, double, double, double, double, bool, bool, int64_t,
+                    int64_t, int64_t, int64_t, int64_t, int64_t, const Tensor&>())
+      .def("set_prof", &MlpStep::set_prof)
+      .def("run", &MlpStep::run)
+      .def("run_many", &MlpStep::run_many, py::call_guard<py::gil_scoped_release>())
+      .def("grid", &MlpStep::grid);
   py::class_<GraphRunner>(m, "GraphRunner")
       .def(py::init<>())
       .def("begin_capture", &GraphRunner::begin_capture)

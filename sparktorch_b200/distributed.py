@@ -137,8 +137,8 @@ def train_distributed(
             try:
                 out = mapPartitionsWithIndex(rdd, make_task(resume or attempt > 0)).collect()
                 break
-            except RuntimeError:
-                if attempt == max_stage_retries or not checkpoint_dir:
+            except Exception as e:      # sparkshim raises RuntimeError, real PySpark Py4JJavaError / PythonException / SparkException
+                if isinstance(e, (KeyboardInterrupt, SystemExit)) or attempt == max_stage_retries or not checkpoint_dir:
                     raise
         state_dict, history = out[0]["state_dict"], out[0]["history"]
         if partition_shuffles - r > 1:

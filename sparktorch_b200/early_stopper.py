@@ -8,8 +8,8 @@ immediately; ``patience == 0`` never stops; ``mode`` is ``min``/``max``;
 
 The state is a plain 4-float record so the very same rule can run on the
 device: :meth:`state_vector` / :meth:`load_state_vector` mirror the struct the
-fused all-reduce kernel updates in-band (csrc/comm/allreduce_opt.cu,
-``EarlyStopState``)."""
+fused kernels update in-band (``StepState`` in csrc/kernels.h: K-AR in
+csrc/comm_ar.cu, the DECIDE task of K-STEP in csrc/mlp_step.cu)."""
 from __future__ import annotations
 
 import math

@@ -89,7 +89,8 @@ class FusedUpdate:
     """Owns the symmetric arenas + the native ``Updater`` for one model replica."""
 
     def __init__(self, numel: int, spec: OptSpec, world: int, rank: int, device: torch.device, patience: int,
-                 max_iters: int, wbf16_elems: int = 0, use_multicast: bool = True, exchange: str = "twoshot"):
+                 max_iters: int, wbf16_elems: int = 0, use_multicast: bool = True, exchange: str = "twoshot",
+                 grad_extra: int = 0):
         C = native.load(required=True)
         self.C = C
         self.numel, self.world, self.rank, self.device = numel, world, rank, device
@@ -98,7 +99,8 @@ class FusedUpdate:
         self.exchange = exchange if world > 1 else "twoshot"
         self.recv_stride = _round_up(numel + TAIL, 64)
         self.block = SymmBlock(device, world, rank)
-        self.block.reserve("grad", (numel + TAIL + 60) * 4)
+        self.grad_extra = grad_extra      # K-STEP partial slots (bias-gradient / loss partials) behind the tail
+        self.block.reserve("grad", (numel + TAIL + 60 + grad_extra) * 4)
         if self.exchange == "push":
             self.block.reserve("recv", 2 * world * self.recv_stride * 4)
         self.block.reserve("param", numel * 4)
@@ -106,7 +108,7 @@ class FusedUpdate:
             self.block.reserve("wbf16", wbf16_elems * 2)
         self.block.reserve("flags", C.flag_words() * 4)
         self.block.rendezvous()
-        self.grad = self.block.view("grad", torch.float32, numel + TAIL)
+        self.grad = self.block.view("grad", torch.float32, numel + TAIL + (60 + grad_extra if grad_extra else 0))
         self.param = self.block.view("param", torch.float32, numel)
         self.wbf16 = self.block.view("wbf16", torch.bfloat16, wbf16_elems) if wbf16_elems else None
         n_state = numel if self.exchange == "push" else opt_state_elems(numel, world)

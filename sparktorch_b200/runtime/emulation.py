@@ -43,9 +43,10 @@ class EmulatedUpdate:
     use_multicast = False
     exchange = "emulated"
 
-    def __init__(self, numel: int, spec: OptSpec, wbf16_elems: int, max_iters: int = 64, weight_dtype=torch.float32):
+    def __init__(self, numel: int, spec: OptSpec, wbf16_elems: int, max_iters: int = 64, weight_dtype=torch.float32,
+                 grad_extra: int = 0):
         self.numel, self.spec = numel, spec
-        self.grad = torch.zeros(numel + TAIL, dtype=torch.float32)
+        self.grad = torch.zeros(numel + TAIL + (60 + grad_extra if grad_extra else 0), dtype=torch.float32)
         self.param = torch.zeros(numel, dtype=torch.float32)
         self.wbf16 = torch.zeros(max(1, wbf16_elems), dtype=weight_dtype)
         self.state = torch.zeros(16, dtype=torch.int32)

@@ -78,7 +78,11 @@ def prepare_targets(Y: Optional[torch.Tensor], criterion) -> Optional[torch.Tens
     if Y is None:
         return None
     if criterion_wants_class_index(criterion):
-        return Y.reshape(-1).long()
+        if Y.dim() == 1 or Y.shape[1] == 1:
+            return Y.reshape(-1).long()
+        # one-hot / probability targets (k columns): CrossEntropyLoss takes them as float class probabilities; the reference
+        # reaches the same call because its first criterion(...) try succeeds for them (distributed.py:152-157)
+        return Y.to(torch.float32)
     return Y
 
 
@@ -213,14 +217,26 @@ def build_comm_and_arena(model: nn.Module, opt_cls, opt_params, cfg: TrainConfig
     spec = parse_optimizer(opt_cls, opt_params)
     patience = cfg.early_stop_patience
     if cfg.comm in ("auto", "p2p") and device.type == "cuda" and spec.kind != "other":
-        try:
+        # The P2P constructor contains collectives (symmetric-memory rendezvous, barrier): either EVERY rank goes that way
+        # or none does.  Only the locally checkable precondition (native extension present) may veto it, and the veto is
+        # agreed on by all ranks BEFORE anyone enters the constructor; a failure inside it is a real error and is raised
+        # (a rank silently falling back to NCCL while its peers spin in the flag barrier would dead-lock the job).
+        from sparktorch_b200.ops import native
+
+        ok = 1 if native.available() else 0
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        if ok:
             from sparktorch_b200.parallel.p2p import P2PFusedComm
 
             comm = P2PFusedComm(model, spec, patience, world, rank, device, cfg.iters)
             return comm, comm.arena
-        except Exception:
-            if cfg.comm == "p2p":
-                raise
+        if cfg.comm == "p2p":
+            raise RuntimeError("comm='p2p' requested but the native extension is unavailable on at least one rank: " + str(native.error()))
     arena = FlatArena(model, device)
     user_opt = None
     if spec.kind == "other":
@@ -316,14 +332,28 @@ def train_partition(
     losses: List[float] = []
     loss_buf = torch.zeros(max(cfg.iters, 1), dtype=torch.float32, device=device)
     start_iter = 0
+    resume_sampler_state = None
     if cfg.resume and cfg.checkpoint_dir:
-        saved = ckpt.load(cfg.checkpoint_dir, rank)
-        if saved is not None and saved.get("numel") == arena.numel:
+        # Every rank must resume from the SAME iteration with the same weights: a crash between two ranks' saves, a
+        # missing / foreign file or a non-shared directory would otherwise let the ranks run different numbers of
+        # exchanges (dead-lock) or train diverged replicas.  Checkpoints keep two generations; the ranks agree on the
+        # newest generation that all of them hold, else everybody restarts from iteration 0.
+        gens = ckpt.load_generations(cfg.checkpoint_dir, rank)
+        gens = {it: pl for it, pl in gens.items() if pl.get("numel") == arena.numel and pl.get("comm_kind", type(comm).__name__) == type(comm).__name__}
+        common = ckpt.agree_on_iteration(sorted(gens), world, device)
+        if common > 0:
+            saved = gens[common]
             with torch.no_grad():
                 arena.flat_p.copy_(saved["flat_p"].to(device))
             comm.import_state(saved["comm"])
             start_iter = int(saved["iters_done"])
             loss_buf[:start_iter] = torch.tensor(saved["losses"][:start_iter], device=device)
+            resume_sampler_state = saved.get("sampler_state")
+        # rank 0's weights win again (they are identical across ranks in every complete generation; this also repairs a
+        # fall-back to iteration 0 after some ranks had already loaded something)
+        comm.broadcast_params()
+    if resume_sampler_state is not None and sampler is not None:
+        sampler.gen.set_state(resume_sampler_state.to("cpu"))
     stopped_at = None
     t_loop = time.time()
 
@@ -333,7 +363,7 @@ def train_partition(
     if world > 1 and getattr(comm, "fused", False):
         from sparktorch_b200.utils.watchdog import ProgressWatchdog
 
-        stall_guard = ProgressWatchdog(lambda: progress[0], label=f"rank {rank} eager loop")
+        stall_guard = ProgressWatchdog(lambda: progress[0], label=f"rank {rank} eager loop", grace_first_s=600.0)
         stall_guard.__enter__()
     try:
         for i in range(start_iter, cfg.iters):
@@ -376,7 +406,8 @@ def train_partition(
                 comm.finish()
                 ckpt.save(cfg.checkpoint_dir, rank, {
                     "numel": arena.numel, "flat_p": arena.flat_p.detach().cpu(), "comm": comm.export_state(),
-                    "iters_done": i + 1, "losses": loss_buf[: i + 1].detach().cpu().tolist()})
+                    "comm_kind": type(comm).__name__, "iters_done": i + 1, "losses": loss_buf[: i + 1].detach().cpu().tolist(),
+                    "sampler_state": None if sampler is None else sampler.gen.get_state()})
         comm.finish()
     finally:
         if stall_guard is not None:

@@ -185,8 +185,11 @@ class FusedMLP:
             # therefore never combined with early stopping (a split stop vote would dead-lock the barrier).
             want = os.environ.get("SPARKTORCH_EXCHANGE", "twoshot")
             push = world > 1 and fuse_loss and want == "push" and patience <= 0
+            from sparktorch_b200.runtime.mega_mlp import mega_extra_elems
+
+            extra = mega_extra_elems(d, [ls.module.bias is not None for ls in lowered.layers], batch)
             self.fu = FusedUpdate(numel, spec, world, rank, device, patience, max_iters, wbf16_elems=off,
-                                  exchange="push" if push else "twoshot")
+                                  exchange="push" if push else "twoshot", grad_extra=extra)
         self.arena = FlatArena(model, device, grad_buffer=self.fu.grad, param_buffer=self.fu.param)
         pos = {id(p): o for p, o in zip(self.arena.params, self.arena.offsets)}
         rows, self.Wb, self.bias, self.gW, self.gb = [], [], [], [], []
@@ -215,6 +218,7 @@ class FusedMLP:
                 self.peer_kw.append({})
         for o in sorted(seg_of):
             rows.append(seg_of[o])
+        self.segment_rows, self.arena_pos = rows, pos          # (K-STEP task builder: runtime/mega_mlp.py)
         if backend_factory is None or getattr(self.fu, "wants_segments", False):
             self.fu.build(rows, zero_grads=True)
         self.loss_slot = self.fu.grad[numel: numel + 1]          # tail[0]: rides in the all-reduce
@@ -482,6 +486,36 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         if windowed:
             plan.window = (windows, Bt)
 
+        # ---- K-STEP: the whole step (and many steps) as ONE persistent kernel launch (csrc/mlp_step.cu)
+        mega = None
+        if (not is_cnn and not is_resnet and nv == 0 and plan.fuse_loss and getattr(plan.fu, "exchange", "") == "twoshot"
+                and os.environ.get("SPARKTORCH_MEGA", "1") == "1"):
+            from sparktorch_b200.parallel.p2p import opt_state_elems
+            from sparktorch_b200.runtime.mega_mlp import MegaPlan
+
+            fu = plan.fu
+            per = opt_state_elems(fu.numel, world)
+            owned = (min(fu.numel, per * rank), min(fu.numel, per * (rank + 1)))
+            blk = fu.block
+            peers = {k: blk.peer_ptrs(k) for k in ("flags", "grad", "param", "wbf16")}
+            if world > 1 and fu.use_multicast:
+                peers["mc"] = {k: blk.multicast_ptr(k) for k in ("grad", "param", "wbf16")}
+            flag_view = blk.view("flags", torch.int32, C.flag_words())
+            if windowed:
+                mx, mt_, mwin = src, tgt_src, (windows, Bt)
+            elif gathered:
+                mx, mt_, mwin = plan.train["acts"][0], plan.train["tgt"], None
+            else:
+                mx, mt_, mwin = src, tgt_src, None
+            mp = MegaPlan(plan, spec, cfg.early_stop_patience, per * rank, owned, mwin, mx, mt_, flag_view, peers=peers,
+                          grid=int(os.environ.get("SPARKTORCH_MEGA_GRID", "148")))
+            if mp.ok:
+                mega = mp
+                mega_step = mp.materialize()
+                if os.environ.get("SPARKTORCH_MEGA_PROF"):      # per-task globaltimer stamps of the last step of a launch
+                    mega_prof = torch.zeros(mp.grid_used * 24 * 8, dtype=torch.int64, device=device)
+                    mega_step.set_prof(mega_prof)
+
         def enqueue_step():
             plan.n_launch = 0
             if gathered:
@@ -494,52 +528,74 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                 plan.forward(plan.val, slot=plan.loss_slot, train=False)
             plan.update()
 
-        # warm-up launch outside capture (module load, smem attributes), then rewind the step state
-        p0 = plan.fu.param.clone()
-        if hasattr(plan, "save_extra"):
-            plan.save_extra()                         # e.g. batch-norm running statistics
-        if streaming:
-            xs[:Bt].copy_(x_host[:Bt].to(device))
-            ys[:Bt].copy_(y_host[:Bt].to(device))
-        enqueue_step()
-        stream.synchronize()
-        plan.fu.param.copy_(p0)
-        if hasattr(plan, "restore_extra"):
-            plan.restore_extra()
-        for t in (plan.fu.m, plan.fu.v):
-            if t is not None:
-                t.zero_()
-        plan.fu.state[2:].zero_()                     # keep epoch/blocks_done, reset step/iter/early-stop record
-        plan.fu.loss_hist.zero_()
-        plan.fu.mailbox.zero_()
-        plan.fu.grad.zero_()
-        plan.fu.updater.publish()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        # Capture the step.  Kernels are launched with programmatic dependent launch so the prologue of
-        # kernel n+1 (barrier init, TMEM alloc, descriptor prefetch) overlaps the tail of kernel n; if the
-        # driver refuses such a capture we fall back to plain stream-ordered edges.
-        use_pdl = os.environ.get("SPARKTORCH_PDL", "1") == "1"
-        for attempt in range(2):
-            C.set_pdl(use_pdl)
-            try:
+        if mega is not None:
+            # nothing to warm up or rewind: the kernel is launched directly (or, when every step needs host-side work -
+            # H2D streaming, a gather kernel - as a 1-step graph that takes its step numbers from the device state)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            use_pdl = False
+            mega_graph = streaming or gathered
+            mega_step.run(0, 0, 0, 0)                    # loads the module / sets the shared-memory attribute (no launch)
+            if mega_graph:
+                if gathered:                             # module load of the gather kernel must not happen inside a capture
+                    C.gather_batch(src, n_src, tgt_src, 0 if kind == "ce" else ytd.shape[1], gmode, ring, seed, Bt, d0,
+                                   plan.train["acts"][0], None, plan.train["tgt"], plan.fu.state)
+                    stream.synchronize()
                 runner.begin_capture()
-                enqueue_step()
+                if gathered:
+                    C.gather_batch(src, n_src, tgt_src, 0 if kind == "ce" else ytd.shape[1], gmode, ring, seed, Bt, d0,
+                                   plan.train["acts"][0], None, plan.train["tgt"], plan.fu.state)
+                mega_step.run(-1, 0, 0, 1)
                 runner.end_capture()
-                break
-            except RuntimeError:
-                C.set_pdl(False)
-                if not use_pdl or attempt == 1:
-                    raise
+            launches = 1 + (1 if gathered else 0)
+        if mega is None:
+            # warm-up launch outside capture (module load, smem attributes), then rewind the step state
+            p0 = plan.fu.param.clone()
+            if hasattr(plan, "save_extra"):
+                plan.save_extra()                         # e.g. batch-norm running statistics
+            if streaming:
+                xs[:Bt].copy_(x_host[:Bt].to(device))
+                ys[:Bt].copy_(y_host[:Bt].to(device))
+            enqueue_step()
+            stream.synchronize()
+            plan.fu.param.copy_(p0)
+            if hasattr(plan, "restore_extra"):
+                plan.restore_extra()
+            for t in (plan.fu.m, plan.fu.v):
+                if t is not None:
+                    t.zero_()
+            plan.fu.state[2:].zero_()                     # keep epoch/blocks_done, reset step/iter/early-stop record
+            plan.fu.loss_hist.zero_()
+            plan.fu.mailbox.zero_()
+            plan.fu.grad.zero_()
+            plan.fu.updater.publish()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            # Capture the step.  Kernels are launched with programmatic dependent launch so the prologue of
+            # kernel n+1 (barrier init, TMEM alloc, descriptor prefetch) overlaps the tail of kernel n; if the
+            # driver refuses such a capture we fall back to plain stream-ordered edges.
+            use_pdl = os.environ.get("SPARKTORCH_PDL", "1") == "1"
+            for attempt in range(2):
+                C.set_pdl(use_pdl)
                 try:
+                    runner.begin_capture()
+                    enqueue_step()
                     runner.end_capture()
+                    break
                 except RuntimeError:
-                    pass
-                runner = C.GraphRunner()
-                use_pdl = False
-        C.set_pdl(False)
-        launches = plan.n_launch
+                    C.set_pdl(False)
+                    if not use_pdl or attempt == 1:
+                        raise
+                    try:
+                        runner.end_capture()
+                    except RuntimeError:
+                        pass
+                    runner = C.GraphRunner()
+                    use_pdl = False
+            C.set_pdl(False)
+            launches = plan.n_launch
         if streaming:
             runner.setup_streaming(x_host.data_ptr(), y_host.data_ptr(), (n // Bt) * Bt, x_host.stride(0) * 2,
                                    y_host.element_size() * (y_host[0].numel() if y_host.dim() > 1 else 1),
@@ -549,6 +605,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         window = WindowTimer(cfg.time_window, device, world)
         mail_ptr = plan.fu.mailbox.data_ptr()
         check = 1 if cfg.verbose else (4 if cfg.early_stop_patience > 0 else 0)
+        steps_per_launch = int(os.environ.get("SPARKTORCH_MEGA_STEPS", "8" if cfg.early_stop_patience > 0 else "64"))
         t_loop = time.time()
         done = 0
         segments = [(0, cfg.iters)]
@@ -570,13 +627,18 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                     window.before_step(lo)
                 if cfg.verbose:
                     for i in range(lo, hi):
-                        got = runner.run(i, 1, mail_ptr, 1)
+                        got = (mega_step.run_many(i, i, i, 1, 1, mail_ptr) if (mega is not None and not mega_graph)
+                               else runner.run(i, 1, mail_ptr, 1))
                         stream.synchronize()
                         done += got
                         print(f"Partition: {rank}. Iteration: {i}. Distributed Loss: {plan.fu.last_loss()}")
                         printed += 1
                         if plan.fu.stopped():
                             break
+                elif mega is not None and not mega_graph:
+                    # steps_per_launch whole steps per kernel launch; the kernel itself idles through the rest of a launch
+                    # once the stop is latched, the host looks at the mailbox between launches
+                    done += mega_step.run_many(lo, lo, lo, hi - lo, steps_per_launch, mail_ptr if check else 0)
                 else:
                     done += runner.run(lo, hi - lo, mail_ptr, check)
                 if timed:
@@ -587,6 +649,18 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         finally:
             wd.__exit__()
     torch.cuda.synchronize(device)
+    if mega is not None and int(mega.d_error[0]) != 0:
+        raise RuntimeError("K-STEP kernel gave up waiting (code, cta, task, epoch) = %s" % mega.d_error.cpu().tolist())
+    if mega is not None and os.environ.get("SPARKTORCH_MEGA_PROF") and rank == 0:
+        import json
+
+        stamps = mega_prof.cpu().view(mega.grid_used, 24, 8).tolist()
+        recs = []
+        for ti, td in enumerate(mega.task_dicts):
+            c, j = mega.cta_of_task[ti]
+            recs.append({"group": td["group"], "cta": c, "slot": j, "m0": td["m0"], "n0": td["n0"], "t": stamps[c][j]})
+        with open(os.environ["SPARKTORCH_MEGA_PROF"], "w") as fh:
+            json.dump({"world": world, "tasks": recs, "info": mega.describe()}, fh)
     t_end = time.time()
     n_done = plan.fu.iters_done()
     if hasattr(plan, "finish"):
@@ -595,11 +669,12 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     losses = plan.fu.loss_hist[:n_done].cpu().tolist()
     history = {
         "engine": "fused_resnet" if is_resnet else ("fused_cnn" if is_cnn else "fused_mlp"),
+        "step_kernel": (dict(mega.describe(), steps_per_launch=1 if mega_graph else steps_per_launch) if mega is not None else None),
         "comm": ("P2PPush" if getattr(plan.fu, "exchange", "") == "push" else "P2PFused" + ("+NVLS" if plan.fu.use_multicast else "")),
         "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
         "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
-        "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes(),
+        "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes() if (mega is None or mega_graph) else 0,
         "streaming": streaming, "sampling": ("stream" if streaming else sampling) if use_mb else "full-batch",
         "fused_loss": plan.fuse_loss, "pdl": use_pdl,
         "h2d_bytes_per_step": (Bt * (_pad(d0) * 2 + (4 if kind == "ce" else 4 * dL))) if streaming else 0,

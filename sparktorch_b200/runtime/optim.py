@@ -4,7 +4,7 @@ The trainers never run ``torch.optim`` in the hot loop (reference:
 distributed.py:198 ``optimizer.step()``, server.py:139).  The optimizer *class*
 and kwargs that travel in the ``TorchObj`` envelope are parsed into an
 :class:`OptSpec`; the update is applied to ONE flat fp32 parameter buffer – by
-the fused all-reduce+update CUDA kernel on B200 (csrc/comm/allreduce_opt.cu) or
+the fused all-reduce+update CUDA kernels on B200 (csrc/comm_ar.cu, csrc/mlp_step.cu) or
 by :func:`apply_update_` below (CPU / oracle path, same math, used by the
 kernel numerics tests).  Semantics follow ``torch.optim.{Adam,AdamW,SGD}``.
 Anything else (``kind == 'other'``) falls back to stepping the user's optimizer

@@ -27,20 +27,35 @@ def default_timeout() -> float:
         return 300.0
 
 
+def _in_driver_process() -> bool:
+    """Barrier task 0 of the single-node runtime runs inline in the user's driver / notebook process."""
+    return os.environ.get("SPARKSHIM_EXECUTOR") != "1" and os.environ.get("SPARKTORCH_WORKER_PROCESS") != "1"
+
+
 def _abort(message: str) -> None:      # pragma: no cover - kills the process
     sys.stderr.write(message + "\n")
     try:
         faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
     finally:
         sys.stderr.flush()
-        os._exit(86)
+    if _in_driver_process():
+        # never take the user's driver / notebook down: make the stuck CUDA call return with an error instead (the
+        # training thread then raises, the stage fails and is retried / reported by the normal path)
+        try:
+            import ctypes
+
+            ctypes.CDLL("libcudart.so").cudaDeviceReset()
+        except Exception:
+            pass
+        return
+    os._exit(86)
 
 
 class ProgressWatchdog:
     """Calls ``on_stall(message)`` when ``get_progress()`` stops changing for ``timeout_s`` seconds."""
 
     def __init__(self, get_progress: Callable[[], int], timeout_s: Optional[float] = None, label: str = "",
-                 on_stall: Callable[[str], None] = _abort, poll_s: float = 1.0):
+                 on_stall: Callable[[str], None] = _abort, poll_s: float = 1.0, grace_first_s: float = 0.0):
         self.get_progress = get_progress
         self.timeout_s = default_timeout() if timeout_s is None else float(timeout_s)
         self.label = label
@@ -49,15 +64,17 @@ class ProgressWatchdog:
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
         self.fired = False
+        self.grace_first_s = grace_first_s      # extra allowance until the FIRST progress (module load, first huge step)
 
     def _run(self) -> None:
         last, since = self.get_progress(), time.monotonic()
+        moved = False
         while not self._stop.wait(self.poll_s):
             cur = self.get_progress()
             now = time.monotonic()
             if cur != last:
-                last, since = cur, now
-            elif now - since >= self.timeout_s:
+                last, since, moved = cur, now, True
+            elif now - since >= self.timeout_s + (0.0 if moved else self.grace_first_s):
                 self.fired = True
                 self.on_stall(f"[sparktorch_b200] {self.label}: no progress for {now - since:.0f} s at iteration {cur} "
                               f"(a peer rank died or a kernel is stuck in a cross-GPU barrier); aborting this task")

@@ -72,12 +72,13 @@ def test_fused_mlp_minibatch_learns_and_counts_launches():
     res = _fit(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=200, mini_batch=256, engine="fused")
     h = res.history
     assert h["engine"] == "fused_mlp" and h["iters_run"] == 200 and h["samples_per_step"] == 256
-    assert h["gpu_launches_per_step"] == 10     # gather + 3 fwd (CE fused in the last) + 3 wgrad + 2 dgrad + update
+    assert h["gpu_launches_per_step"] == 2      # gather + the K-STEP kernel (whole step)
     assert h["fused_loss"] and h["sampling"] == "random"
     res2 = _fit(mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, iters=200, mini_batch=256,
                 engine="fused", sampling="sweep")
     h2 = res2.history
-    assert h2["gpu_launches_per_step"] == 9 and h2["sampling"] == "sweep"    # no gather kernel: windows taken in-kernel
+    assert h2["gpu_launches_per_step"] == 1 and h2["sampling"] == "sweep"    # no gather kernel: windows taken in-kernel
+    assert h2["step_kernel"]["steps_per_launch"] == 64 and h["step_kernel"]["steps_per_launch"] == 1
     assert np.mean(h2["train_loss"][-20:]) < 0.6 * np.mean(h2["train_loss"][:5])
     assert np.mean(h["train_loss"][-20:]) < 0.6 * np.mean(h["train_loss"][:5])
 
