@@ -25,6 +25,16 @@ def main(path, md=None):
         lines.append(f"| {k} | {len(v)} | " + " | ".join(cells) + " |")
     end = max(x for t in ts for x in t["t"] if x)
     out = [f"K-STEP timeline (us from the first stamp; world={p.get('world')}, {p['info']}); step span {(end - t0) / 1000:.1f} us", ""] + lines
+    # per-k-block view of the first task of a few groups: B issued / A issued / stage landed, relative to the task's "deps"
+    for grp in ("F1", "F2", "B2", "G1"):
+        for t in p["tasks"]:
+            if t["group"] == grp and t.get("kb"):
+                base = t["t"][0]
+                rows = ["%d:%s" % (i, "/".join("%.2f" % ((x - base) / 1000) if x else "-" for x in kb[:3])) for i, kb in enumerate(t["kb"])]
+                out.append("")
+                out.append(f"{grp} cta {t['cta']} k-blocks (B issued/A issued/landed, us after the task's wait start; deps at "
+                           f"{(t['t'][2] - base) / 1000:.2f}): " + "  ".join(rows))
+                break
     print("\n".join(out))
     if md:
         open(md, "w").write("\n".join(out) + "\n")

@@ -9,7 +9,10 @@ the Spark layer, so the extension can be built and the kernels used on a box
 without any Spark API on ``sys.path``."""
 import importlib
 
+from sparktorch_b200._spark import locate_pyspark
+
 __version__ = "0.2.0"
+locate_pyspark()          # sys.path only; nothing of Spark is imported here
 
 _LAZY = {
     "serialize_torch_obj": "sparktorch_b200.util",

@@ -10,6 +10,15 @@ import sys
 _SHIM_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sparkshim")
 
 
+def locate_pyspark() -> None:
+    """Make ``import pyspark`` resolvable (real package, else the in-repo runtime) WITHOUT importing it: only sys.path is
+    touched, so ``import sparktorch_b200`` stays cheap and scripts that import pyspark right after it keep working."""
+    if "pyspark" in sys.modules:
+        return
+    if importlib.util.find_spec("pyspark") is None and _SHIM_DIR not in sys.path:
+        sys.path.append(_SHIM_DIR)
+
+
 def ensure_pyspark() -> str:
     """Returns 'pyspark' or 'sparkshim'."""
     if "pyspark" in sys.modules:

@@ -501,6 +501,15 @@ class MlpStep {
     p_.n_mt = int(n_mt); p_.loss_off = loss_off; p_.window_rows = window_rows; p_.n_windows = n_windows > 0 ? n_windows : 1;
     p_.error = reinterpret_cast<uint32_t*>(error.data_ptr<int32_t>());
   }
+  void set_prof_kb(const OptT& prof) {
+    prof_kb_ = prof;
+    if (prof) {
+      TORCH_CHECK(prof->is_cuda() && prof->scalar_type() == at::kLong && prof->numel() >= int64_t(grid_) * st::MS_MAX_TASKS * 64);
+      p_.prof_kb = reinterpret_cast<long long*>(prof->data_ptr());
+    } else {
+      p_.prof_kb = nullptr;
+    }
+  }
   void set_prof(const OptT& prof) {
     prof_ = prof;
     if (prof) {
@@ -534,7 +543,7 @@ class MlpStep {
   st::MsParams p_;
   int grid_ = 0;
   Tensor tasks_, n_tasks_, tmaps_, peers_, counters_, segs_, state_, error_;
-  OptT m_, v_, loss_hist_, prof_;
+  OptT m_, v_, loss_hist_, prof_, prof_kb_;
 };
 int64_t ms_task_bytes() { return int64_t(sizeof(st::MsTask)); }
 int64_t ms_max_tasks() { return st::MS_MAX_TASKS; }
@@ -726,6 +735,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     const OptT&, int64_t, int64_t, double, double, double, double, double, double, double, bool, bool, int64_t,
                     int64_t, int64_t, int64_t, int64_t, int64_t, const Tensor&>())
       .def("set_prof", &MlpStep::set_prof)
+      .def("set_prof_kb", &MlpStep::set_prof_kb)
       .def("run", &MlpStep::run)
       .def("run_many", &MlpStep::run_many, py::call_guard<py::gil_scoped_release>())
       .def("grid", &MlpStep::grid);

@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const MsParams 
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_ptr;
   long long* prof = p.prof ? p.prof + size_t(blockIdx.x) * MS_MAX_TASKS * 8 : nullptr;
+  long long* prof_kb = p.prof_kb ? p.prof_kb + size_t(blockIdx.x) * MS_MAX_TASKS * 64 : nullptr;
 
   if (warp == 0) {
     // ===================== dependency waits + TMA producer =====================
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const MsParams 
             const int k0 = i * MS_BLOCK_K;
             if (b_mn) tma_load_2d(sb, mb, &sh->full_bar[st_], n0, k0 + b_k_off);
             else tma_load_2d(sb, mb, &sh->full_bar[st_], k0, n0);
+            if (stamp && prof_kb && i < 16) prof_kb[ti * 64 + i * 4 + 0] = (long long)globaltimer_ns();
           }
         }
         // -- late: the A operand (what the previous phase of this step produced)
@@ -506,6 +508,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const MsParams 
             } else {
               tma_load_2d(sa, ma, &sh->full_bar[st_], k0, m0 + a_row_off);
             }
+            if (stamp && prof_kb && i < 16) prof_kb[ti * 64 + i * 4 + 1] = (long long)globaltimer_ns();
           }
         }
         __syncwarp();
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const MsParams 
             ms_mbar_wait(&sh->full_bar[st_], ph, p, 12);
             tc_fence_after();
             if (i == 0 && p.prof != nullptr && s == p.n_steps - 1) prof[ti * 8 + 3] = (long long)globaltimer_ns();
+            if (prof_kb != nullptr && s == p.n_steps - 1 && i < 16) prof_kb[ti * 64 + i * 4 + 2] = (long long)globaltimer_ns();
             const uint32_t sa = smem_u32(smem + st_ * MS_STAGE_BYTES);
             const uint32_t sb = sa + MS_A_BYTES;
             const uint64_t da = a_mn ? make_mnmajor_sw128_desc(sa, MS_BLOCK_K * 128) : make_kmajor_sw128_desc(sa);

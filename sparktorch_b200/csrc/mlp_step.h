@@ -102,7 +102,8 @@ struct MsParams {
   int64_t step0;           // optimizer steps applied before the first step
   uint32_t epoch0;         // steps run since the counters/flags were zeroed
   int n_steps;
-  long long* prof;         // optional [grid][MS_MAX_TASKS][4] globaltimer stamps of the last step
+  long long* prof;         // optional [grid][MS_MAX_TASKS][8] globaltimer stamps of the last step
+  long long* prof_kb;      // optional [grid][MS_MAX_TASKS][16][4]: per k-block B issued, A issued, stage landed (MMA thread), unused
   uint32_t* error;         // [4] device word set before a trap: code, cta, task, epoch
 };
 

@@ -1,0 +1,310 @@
+"""Op substitution for ARBITRARY user modules.
+
+The reference trains whatever ``nn.Module`` arrives in the dill envelope
+(/root/reference/sparktorch/distributed.py:112-120,150,176).  Models that lower to one of the fully fused
+plans (runtime/fused_*.py) never reach this file.  Everything else keeps running under autograd - but its
+GEMM-shaped work is re-routed to our sm_100a kernels instead of cuBLAS/cuDNN:
+
+    nn.Linear        forward / dgrad / wgrad on the tcgen05 GEMM (csrc/gemm_sm100.cu), bias fused in the epilogue,
+                     the weight gradient accumulated straight into the parameter's ``.grad`` view of the flat arena
+    nn.Conv2d        im2col (csrc/conv.cu) + the same GEMM for forward, dgrad and wgrad (groups = 1, dilation = 1)
+    CrossEntropyLoss / NLLLoss(log_softmax) / MSELoss (mean reduction, no weights)
+                     one fused forward+backward pass (csrc/loss.cu)
+
+Elementwise / normalisation / pooling layers (ReLU, Tanh, Softmax, BatchNorm, ...) stay ATen kernels: they are not
+library GEMMs and cost one memory pass.  Parameters are untouched fp32 views of the flat arena, so the ``state_dict``
+that goes back to the driver loads into the user's original module.
+
+``swap_modules`` returns a report; ``report["library_gemm_modules"]`` lists what is still served by cuBLAS/cuDNN
+(grouped / dilated / transposed convolutions, RNNs, attention, bilinear ...).  Substitution is per module instance
+(``forward`` is rebound), reversible with ``unswap_modules``.
+"""
+from __future__ import annotations
+
+import types
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from sparktorch_b200.ops import native
+
+
+def _pad(n: int, m: int = 8) -> int:
+    return (n + m - 1) // m * m
+
+
+def _bf16_rows(x2: torch.Tensor) -> torch.Tensor:
+    """[M, K] any float dtype -> bf16 [M, pad8(K)][:, :K] (16-byte aligned rows; the pad is never read: TMA bounds = K)."""
+    M, K = x2.shape
+    if x2.dtype == torch.bfloat16 and x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0:
+        return x2
+    buf = torch.empty(M, _pad(K), dtype=torch.bfloat16, device=x2.device)
+    out = buf[:, :K]
+    out.copy_(x2)
+    return out
+
+
+def _f32_out(M: int, N: int, device) -> torch.Tensor:
+    return torch.empty(M, _pad(N, 4), dtype=torch.float32, device=device)[:, :N]
+
+
+class _WeightCache:
+    """bf16 copy of a weight matrix, refreshed when the fp32 master changed (the update kernel bumps nothing, so the
+    engine calls ``invalidate()`` after every optimizer step; ``_version`` catches in-place edits by user code)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.version = -1
+        self.stamp = -1
+
+    def get(self, w2: torch.Tensor, version: int, stamp: int) -> torch.Tensor:
+        if self.buf is None or self.version != version or self.stamp != stamp or self.buf.shape != w2.shape:
+            self.buf = _bf16_rows(w2.detach())
+            self.version, self.stamp = version, stamp
+        return self.buf
+
+
+_STEP_STAMP = [0]
+
+
+def invalidate_weight_caches() -> None:
+    """Called by the engine after every parameter update (the fused update kernels write the arena directly)."""
+    _STEP_STAMP[0] += 1
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache):
+        C = native.load(required=True)
+        N, K = weight.shape
+        lead = x.shape[:-1]
+        xa = _bf16_rows(x.reshape(-1, K))
+        M = xa.shape[0]
+        wb = cache.get(weight, weight._version, _STEP_STAMP[0])
+        out = _f32_out(M, N, x.device)
+        C.gemm_bf16(xa, False, wb, False, M, N, K, bias=bias.detach() if bias is not None else None, out_f32=out)
+        ctx.save_for_backward(xa, wb)
+        ctx.weight, ctx.has_bias, ctx.lead = weight, bias is not None, lead
+        ctx.in_dtype = x.dtype
+        return out.reshape(*lead, N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        C = native.load(required=True)
+        xa, wb = ctx.saved_tensors
+        weight = ctx.weight
+        N, K = weight.shape
+        M = xa.shape[0]
+        g2 = gy.reshape(M, N)
+        gb = _bf16_rows(g2)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dX[M, K] = dY[M, N] W[N, K]: W is the B operand stored [reduction rows, K contiguous] = MN-major
+            dxo = _f32_out(M, K, gy.device)
+            C.gemm_bf16(gb, False, wb, True, M, K, N, out_f32=dxo)
+            dx = dxo.reshape(*ctx.lead, K).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            # dW[N, K] = dY^T X: both operands as stored (MN-major), reduction over the M rows
+            g = weight.grad
+            if g is not None and g.is_contiguous() and g.dtype == torch.float32 and K % 4 == 0:
+                # accumulate straight into the parameter's gradient (a view of the flat arena the update kernel reduces)
+                C.gemm_bf16(gb, True, xa, True, N, K, M, out_f32=g.view(N, K), atomic_f32=True)
+            else:
+                dwo = _f32_out(N, K, gy.device)
+                C.gemm_bf16(gb, True, xa, True, N, K, M, out_f32=dwo)
+                dw = dwo
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g2.sum(dim=0)
+        return dx, dw, db, None
+
+
+def _linear_forward(self, x):
+    if not x.is_cuda or x.shape[-1] != self.in_features or x.numel() == 0:
+        return F.linear(x, self.weight, self.bias)
+    return _LinearFn.apply(x, self.weight, self.bias, self._st_cache)
+
+
+# ------------------------------------------------------------------------------------------------- convolution
+class _Conv2dFn(torch.autograd.Function):
+    """Implicit GEMM over an explicit patch matrix: col[B*OH*OW, Cin*kh*kw] (csrc/conv.cu im2col_nhwc, (c, i, j) column order
+    = torch's weight layout), Y = col W^T.  dgrad = col2im of dY W (fold), wgrad = dY^T col."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache, stride, padding):
+        C = native.load(required=True)
+        B, Cin, H, W = x.shape
+        Cout, _, kh, kw = weight.shape
+        OH, OW = (H + 2 * padding - kh) // stride + 1, (W + 2 * padding - kw) // stride + 1
+        K = Cin * kh * kw
+        xb = x.detach().to(torch.bfloat16).contiguous()                       # NCHW bf16; im2col addresses it through strides
+        col = torch.empty(B * OH * OW, _pad(K), dtype=torch.bfloat16, device=x.device)[:, :K]
+        C.im2col_nhwc(xb, B, H, W, Cin, Cin * H * W, W, 1, H * W, kh, kw, stride, padding, col)
+        wb = cache.get(weight.reshape(Cout, K), weight._version, _STEP_STAMP[0])
+        out = _f32_out(B * OH * OW, Cout, x.device)
+        C.gemm_bf16(col, False, wb, False, B * OH * OW, Cout, K, bias=bias.detach() if bias is not None else None, out_f32=out)
+        ctx.save_for_backward(col, wb)
+        ctx.weight, ctx.has_bias, ctx.geo = weight, bias is not None, (B, Cin, H, W, Cout, kh, kw, OH, OW, stride, padding)
+        ctx.in_dtype = x.dtype
+        return out.reshape(B, OH, OW, Cout).permute(0, 3, 1, 2)               # NCHW view of the NHWC result
+
+    @staticmethod
+    def backward(ctx, gy):
+        C = native.load(required=True)
+        col, wb = ctx.saved_tensors
+        weight = ctx.weight
+        B, Cin, H, W, Cout, kh, kw, OH, OW, stride, padding = ctx.geo
+        K = Cin * kh * kw
+        M = B * OH * OW
+        g2 = gy.permute(0, 2, 3, 1).reshape(M, Cout)
+        gb = _bf16_rows(g2)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dcol = _f32_out(M, K, gy.device)
+            C.gemm_bf16(gb, False, wb, True, M, K, Cout, out_f32=dcol)
+            # col2im: overlapping patches add up (ATen fold = scatter-add, not a GEMM)
+            dx = F.fold(dcol.reshape(B, OH * OW, K).transpose(1, 2), (H, W), (kh, kw), padding=padding, stride=stride).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            g = weight.grad
+            if g is not None and g.is_contiguous() and g.dtype == torch.float32 and K % 4 == 0:
+                C.gemm_bf16(gb, True, col, True, Cout, K, M, out_f32=g.view(Cout, K), atomic_f32=True)
+            else:
+                dwo = _f32_out(Cout, K, gy.device)
+                C.gemm_bf16(gb, True, col, True, Cout, K, M, out_f32=dwo)
+                dw = dwo.reshape(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g2.sum(dim=0)
+        return dx, dw, db, None, None, None
+
+
+def _conv_ok(m: nn.Conv2d) -> bool:
+    one = lambda v: v[0] if isinstance(v, (tuple, list)) else v      # noqa: E731
+    same = lambda v: not isinstance(v, (tuple, list)) or len(set(v)) == 1      # noqa: E731
+    return (m.groups == 1 and one(m.dilation) == 1 and same(m.dilation) and same(m.stride) and same(m.padding)
+            and not isinstance(m.padding, str) and m.padding_mode == "zeros" and type(m) is nn.Conv2d)
+
+
+def _conv_forward(self, x):
+    if not x.is_cuda or x.dim() != 4 or x.numel() == 0:
+        return self._conv_forward(x, self.weight, self.bias)
+    one = lambda v: v[0] if isinstance(v, (tuple, list)) else v      # noqa: E731
+    return _Conv2dFn.apply(x, self.weight, self.bias, self._st_cache, one(self.stride), one(self.padding))
+
+
+# ------------------------------------------------------------------------------------------------- losses
+class _SoftmaxCEFn(torch.autograd.Function):
+    """mean softmax cross entropy: one pass produces the loss and dlogits (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        C = native.load(required=True)
+        B, K = logits.shape
+        z = logits.detach().to(torch.float32)
+        if z.stride(1) != 1:
+            z = z.contiguous()
+        slot = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        dz = torch.empty(B, _pad(K), dtype=torch.bfloat16, device=logits.device)
+        C.softmax_ce(z, target.to(torch.int32), K, slot, dz, None, None, _pad(K))
+        ctx.save_for_backward(dz)
+        ctx.K, ctx.dtype = K, logits.dtype
+        return slot[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz[:, : ctx.K].to(ctx.dtype) * g), None
+
+
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        C = native.load(required=True)
+        B, D = pred.shape
+        p = pred.detach().to(torch.float32)
+        t = target.detach().to(torch.float32)
+        if p.stride(1) != 1:
+            p = p.contiguous()
+        if t.stride(1) != 1:
+            t = t.contiguous()
+        slot = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        dz = torch.empty(B, _pad(D), dtype=torch.bfloat16, device=pred.device)
+        C.mse_loss(p, t, D, slot, dz, None, None, _pad(D))
+        ctx.save_for_backward(dz)
+        ctx.D, ctx.dtype = D, pred.dtype
+        return slot[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz[:, : ctx.D].to(ctx.dtype) * g), None
+
+
+class _SwappedCriterion(nn.Module):
+    def __init__(self, inner, kind: str):
+        super().__init__()
+        self.inner, self.kind = inner, kind
+
+    def forward(self, out, target):
+        ok = out.is_cuda and out.dim() == 2 and out.shape[0] > 0
+        if self.kind == "ce" and ok and target.dim() == 1 and not target.is_floating_point():
+            return _SoftmaxCEFn.apply(out, target)
+        if self.kind == "nll" and ok and target.dim() == 1 and not target.is_floating_point():
+            # NLL of log-probabilities == CE of the same values re-normalised (log_softmax is idempotent)
+            return _SoftmaxCEFn.apply(out, target)
+        if self.kind == "mse" and ok and target.shape == out.shape:
+            return _MSEFn.apply(out, target)
+        return self.inner(out, target)
+
+
+def _swap_criterion(criterion):
+    if isinstance(criterion, nn.CrossEntropyLoss) and criterion.weight is None and criterion.reduction == "mean" \
+            and not getattr(criterion, "label_smoothing", 0.0) and criterion.ignore_index == -100:
+        return _SwappedCriterion(criterion, "ce"), "softmax_ce"
+    if isinstance(criterion, nn.NLLLoss) and criterion.weight is None and criterion.reduction == "mean" and criterion.ignore_index == -100:
+        return _SwappedCriterion(criterion, "nll"), "softmax_ce(nll)"
+    if isinstance(criterion, nn.MSELoss) and criterion.reduction == "mean":
+        return _SwappedCriterion(criterion, "mse"), "mse"
+    return criterion, None
+
+
+_LIBRARY_GEMM_TYPES = (nn.Conv1d, nn.Conv2d, nn.Conv3d, nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d, nn.Linear,
+                       nn.Bilinear, nn.RNNBase, nn.RNNCellBase, nn.MultiheadAttention, nn.Transformer, nn.LazyLinear)
+
+
+def swap_modules(model: nn.Module, criterion, precision: str = "auto") -> Tuple[nn.Module, Any, Dict[str, Any]]:
+    """Rebind ``forward`` of every nn.Linear / eligible nn.Conv2d instance to the sm_100a implementation and wrap the
+    criterion.  bf16 tensor-core compute with fp32 accumulation, fp32 parameters; ``precision='fp32'`` disables it."""
+    report: Dict[str, Any] = {"linear": 0, "conv2d": 0, "criterion": None, "library_gemm_modules": []}
+    if precision == "fp32" or not native.available():
+        report["disabled"] = "precision=fp32" if precision == "fp32" else str(native.error())
+        report["library_gemm_modules"] = [n for n, m in model.named_modules() if isinstance(m, _LIBRARY_GEMM_TYPES)]
+        return model, criterion, report
+    for name, m in model.named_modules():
+        if type(m) is nn.Linear:
+            m._st_cache = _WeightCache()
+            m._st_orig_forward = m.forward
+            m.forward = types.MethodType(_linear_forward, m)
+            report["linear"] += 1
+        elif isinstance(m, nn.Conv2d) and _conv_ok(m):
+            m._st_cache = _WeightCache()
+            m._st_orig_forward = m.forward
+            m.forward = types.MethodType(_conv_forward, m)
+            report["conv2d"] += 1
+        elif isinstance(m, _LIBRARY_GEMM_TYPES):
+            report["library_gemm_modules"].append(name or type(m).__name__)
+    criterion, kind = _swap_criterion(criterion)
+    report["criterion"] = kind
+    return model, criterion, report
+
+
+def unswap_modules(model: nn.Module) -> None:
+    for m in model.modules():
+        if hasattr(m, "_st_orig_forward"):
+            try:
+                del m.forward           # drop the instance attribute: the class method is back
+            except AttributeError:
+                pass
+            del m._st_orig_forward
+            if hasattr(m, "_st_cache"):
+                del m._st_cache

@@ -203,6 +203,18 @@ class P2PFusedComm:
             return StepResult(self.fu.last_loss(), stop)
         return StepResult(None, False)
 
+    def after_graph_step(self, need_loss: bool):
+        """Bookkeeping of a step whose K-AR launch was part of a replayed CUDA graph (runtime/engine.py GraphedStep)."""
+        from sparktorch_b200.parallel.comm import StepResult
+
+        self.step_count += 1
+        if need_loss or self.patience > 0:
+            torch.cuda.current_stream(self.fu.device).synchronize()
+            stop = self.fu.stopped()
+            self.stopped = stop
+            return StepResult(self.fu.last_loss(), stop)
+        return StepResult(None, False)
+
     def finish(self) -> None:
         torch.cuda.synchronize(self.fu.device)
 

@@ -16,7 +16,9 @@ SURVEY.md §3.1).  Differences by design:
 Two step implementations share this loop:
 
 * ``EagerStep``  – autograd over the user's module (any ``nn.Module``), CPU or
-  GPU, with our Linear/Conv2d/CE kernels swapped in on B200 when available;
+  GPU; on B200 the Linear / Conv2d / CE / MSE work is substituted by our kernels
+  (ops/module_swap.py) and the whole step is replayed as one CUDA graph
+  (``GraphedStep``);
 * ``FusedMLPStep`` (runtime/fused_mlp.py) – recognised MLP + CE/MSE + Adam/SGD
   runs as a CUDA graph of hand-written sm_100a kernels, no autograd, no Python
   in the loop.
@@ -172,6 +174,101 @@ class EagerStep:
             self.model.train(was_training)
 
 
+class GraphedStep:
+    """One training step of the eager engine (any nn.Module under autograd, GEMMs on our kernels through
+    ops/module_swap.py, the fused K-AR update) captured into a CUDA graph and replayed: no Python, no per-op launch
+    overhead in the loop.  Static input tensors are refilled before every replay.  Falls back (``capture() -> False``)
+    when the module cannot be captured (host syncs, data-dependent control flow, ...)."""
+
+    def __init__(self, step: "EagerStep", comm, arena: FlatArena, x_all, y_all, x_val, y_val, batch: int, static_input: bool,
+                 device: torch.device):
+        self.step, self.comm, self.arena, self.device = step, comm, arena, device
+        self.x_val, self.y_val = x_val, y_val
+        self.static_input = static_input          # full batch: the resident partition IS the input
+        if static_input:
+            self.sx, self.sy = x_all, y_all
+        else:
+            self.sx = torch.zeros((batch,) + tuple(x_all.shape[1:]), dtype=x_all.dtype, device=device)
+            self.sy = self.sx if y_all is x_all else torch.zeros((batch,) + tuple(y_all.shape[1:]), dtype=y_all.dtype, device=device)
+        self.loss = torch.zeros((), dtype=torch.float32, device=device)
+        self.val_loss = torch.zeros((), dtype=torch.float32, device=device) if x_val is not None else None
+        self.graph = None
+
+    def _body(self) -> None:
+        from sparktorch_b200.ops.module_swap import invalidate_weight_caches
+
+        invalidate_weight_caches()                 # the bf16 weight casts must be part of every replay
+        loss = self.step.run(self.sx, self.sy)
+        self.loss.copy_(loss)
+        if self.x_val is not None:
+            v = self.step.evaluate(self.x_val, self.y_val)
+            self.val_loss.copy_(v)
+            self.arena.tail[0] = v
+        else:
+            self.arena.tail[0] = loss
+        self.comm.fu.updater.step()
+
+    def capture(self, world: int) -> bool:
+        fu = self.comm.fu
+        saved = {"param": fu.param.clone(), "state": fu.state.clone(), "m": None if fu.m is None else fu.m.clone(),
+                 "v": None if fu.v is None else fu.v.clone()}
+        bufs = [b.clone() for b in self.step.model.buffers()]
+        ok = True
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                 # warm-up on a side stream (autograd / allocator settle), as torch.cuda.graphs asks for
+                    self._body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        except Exception as e:                     # not capturable: run the plain eager loop
+            self.error = repr(e)
+            ok = False
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:
+                pass
+        # every rank must take the same path (the captured step contains the cross-GPU exchange)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(int(t.item()))
+        # rewind what warm-up and capture changed: weights, optimizer state, step state, loss history, statistics buffers
+        with torch.no_grad():
+            fu.param.copy_(saved["param"])
+            if fu.m is not None:
+                fu.m.copy_(saved["m"])
+            if fu.v is not None:
+                fu.v.copy_(saved["v"])
+            fu.state[2:].copy_(saved["state"][2:])
+            fu.loss_hist.zero_()
+            fu.mailbox.zero_()
+            fu.grad.zero_()
+            for b, b0 in zip(self.step.model.buffers(), bufs):
+                b.copy_(b0)
+        torch.cuda.synchronize(self.device)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        return ok
+
+    def replay(self, xb, yb):
+        if not self.static_input:
+            self.sx.copy_(xb, non_blocking=True)
+            if self.sy is not self.sx:
+                self.sy.copy_(yb, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.val_loss
+
+
 class DeviceSampler:
     """Mini-batch index sampler living on the training device (no host sync)."""
 
@@ -304,16 +401,18 @@ def train_partition(
     model.train()
     if hasattr(criterion, "to"):
         criterion = criterion.to(device)
+    swap_report = None
     if device.type == "cuda" and cfg.engine != "eager_plain":
-        try:  # swap in our sm_100a Linear/Conv2d/CE autograd functions where they apply
-            from sparktorch_b200.ops.module_swap import swap_modules
+        # GEMM-shaped work of ANY module goes to our sm_100a kernels (ops/module_swap.py): Linear / Conv2d forward, dgrad,
+        # wgrad on the tcgen05 GEMM, fused CE / MSE; the rest of the module runs as it is under autograd
+        from sparktorch_b200.ops.module_swap import swap_modules
 
-            model, criterion = swap_modules(model, criterion, precision=cfg.precision)
-        except ImportError:
-            pass
+        model, criterion, swap_report = swap_modules(model, criterion, precision=cfg.precision)
+    swapped = swap_report is not None and (swap_report["linear"] + swap_report["conv2d"]) > 0
     comm, arena = build_comm_and_arena(model, opt_cls, opt_params, cfg, world, rank, device)
     comm.broadcast_params()
-    step = EagerStep(model, criterion, arena, autocast_bf16=(cfg.precision == "bf16" and device.type == "cuda"))
+    # (swapped modules do their own bf16 casts; torch.autocast is only for the un-swapped eager path)
+    step = EagerStep(model, criterion, arena, autocast_bf16=(cfg.precision == "bf16" and device.type == "cuda" and not swapped))
 
     n = x_all.shape[0]
     use_mb = 0 < cfg.mini_batch < n
@@ -365,6 +464,13 @@ def train_partition(
 
         stall_guard = ProgressWatchdog(lambda: progress[0], label=f"rank {rank} eager loop", grace_first_s=600.0)
         stall_guard.__enter__()
+    graphed = None
+    if (device.type == "cuda" and getattr(comm, "fused", False) and cfg.engine != "eager_plain" and not cfg.checkpoint_dir
+            and __import__("os").environ.get("SPARKTORCH_EAGER_GRAPH", "1") == "1"):
+        bsz = cfg.mini_batch if use_mb else n
+        graphed = GraphedStep(step, comm, arena, x_all, y_all, x_val, y_val, bsz, static_input=not use_mb, device=device)
+        if not graphed.capture(world):
+            graphed = None
     try:
         for i in range(start_iter, cfg.iters):
             progress[0] = i
@@ -383,14 +489,24 @@ def train_partition(
                     yb = xb
             else:
                 xb, yb = x_all, y_all
-            with tracer.phase("forward_backward"):
-                loss = step.run(xb, yb)
-            val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
-            # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
-            arena.tail[0] = val_loss if val_loss is not None else loss
-            loss_buf[i] = loss
-            with tracer.phase("exchange_update"):
-                res = comm.reduce_and_update(need_loss)
+            if graphed is not None:
+                # the whole step (autograd forward/backward through the swapped kernels, validation forward, K-AR) is ONE graph
+                loss, val_loss = graphed.replay(xb, yb)
+                loss_buf[i].copy_(loss)
+                res = comm.after_graph_step(need_loss)
+            else:
+                with tracer.phase("forward_backward"):
+                    loss = step.run(xb, yb)
+                val_loss = step.evaluate(x_val, y_val) if x_val is not None else None
+                # piggy-back: loss used for early stopping is val loss when present (distributed.py:187)
+                arena.tail[0] = val_loss if val_loss is not None else loss
+                loss_buf[i] = loss
+                with tracer.phase("exchange_update"):
+                    res = comm.reduce_and_update(need_loss)
+                if swapped:
+                    from sparktorch_b200.ops.module_swap import invalidate_weight_caches
+
+                    invalidate_weight_caches()
             if host_loss is not None:     # per-step device→host read of the step result
                 host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
                 d2h_bytes = 4
@@ -419,7 +535,9 @@ def train_partition(
     comm.average_buffers(model)
     t_end = time.time()
     history = {
-        "engine": step.name,
+        "engine": step.name + ("+graph" if graphed is not None else ""),
+        "kernel_swap": swap_report,
+        "library_kernels": (swap_report is None or bool(swap_report.get("library_gemm_modules")) or bool(swap_report.get("disabled"))) if device.type == "cuda" else None,
         "comm": type(comm).__name__,
         "world_size": world,
         "train_loss": losses,

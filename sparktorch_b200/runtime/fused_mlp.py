@@ -515,6 +515,8 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                 if os.environ.get("SPARKTORCH_MEGA_PROF"):      # per-task globaltimer stamps of the last step of a launch
                     mega_prof = torch.zeros(mp.grid_used * 24 * 8, dtype=torch.int64, device=device)
                     mega_step.set_prof(mega_prof)
+                    mega_prof_kb = torch.zeros(mp.grid_used * 24 * 64, dtype=torch.int64, device=device)
+                    mega_step.set_prof_kb(mega_prof_kb)
 
         def enqueue_step():
             plan.n_launch = 0
@@ -655,10 +657,12 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         import json
 
         stamps = mega_prof.cpu().view(mega.grid_used, 24, 8).tolist()
+        kbs = mega_prof_kb.cpu().view(mega.grid_used, 24, 16, 4).tolist()
         recs = []
         for ti, td in enumerate(mega.task_dicts):
             c, j = mega.cta_of_task[ti]
-            recs.append({"group": td["group"], "cta": c, "slot": j, "m0": td["m0"], "n0": td["n0"], "t": stamps[c][j]})
+            recs.append({"group": td["group"], "cta": c, "slot": j, "m0": td["m0"], "n0": td["n0"], "t": stamps[c][j],
+                         "kb": kbs[c][j][: max(1, min(16, td["num_kb"]))]})
         with open(os.environ["SPARKTORCH_MEGA_PROF"], "w") as fh:
             json.dump({"world": world, "tasks": recs, "info": mega.describe()}, fh)
     t_end = time.time()
