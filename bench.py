@@ -64,15 +64,27 @@ MODEL_NAME = {"dnn": "MNIST-DNN 784-256-256-10 CE Adam(lr=1e-3)",
 
 
 def synthetic_mnist(n_rows: int, seed: int):
-    """Pixel-like synthetic rows: integer intensities 0..255 (exact in bf16),
-    ~80 % zeros like real MNIST, labels 0..9."""
+    """Pixel-like synthetic rows: intensities k/256, k = 0..255 (exact in bf16), ~80 % zeros like real MNIST.  Labels come
+    from a fixed random linear teacher over the pixels, so there is something to learn: both arms report their first / last
+    loss and a run whose loss does not fall is rejected (a wrong update must not pass as a fast one)."""
     import numpy as np
 
     rng = np.random.default_rng(seed)
     x = rng.integers(0, 256, size=(n_rows, IN_FEATURES), dtype=np.uint8)
     x *= (rng.random((n_rows, IN_FEATURES), dtype=np.float32) < 0.2).astype(np.uint8)
-    y = rng.integers(0, N_CLASSES, size=n_rows).astype(np.float64)
+    x = x.astype(np.float32) / 256.0
+    teacher = np.random.default_rng(4242).normal(size=(IN_FEATURES, N_CLASSES)).astype(np.float32)
+    y = np.empty(n_rows, dtype=np.float64)
+    for s0 in range(0, n_rows, 65536):
+        y[s0:s0 + 65536] = (x[s0:s0 + 65536] @ teacher).argmax(1)
     return x, y
+
+
+def loss_record(first, last):
+    import math
+
+    ok = bool(first is not None and last is not None and math.isfinite(first) and math.isfinite(last) and last < first)
+    return {"first": first, "last": last, "finite_and_decreasing": ok}
 
 
 def emit(obj):
@@ -92,7 +104,7 @@ def run_reference(args):
     import torch
     import torch.nn as nn
 
-    from baseline.ref_harness import TimedAdam, install_backend_patch
+    from baseline.ref_harness import LoggedCrossEntropy, TimedAdam, install_backend_patch
     from sparktorch_b200.utils.clocks import ClockSampler
 
     if not torch.cuda.is_available() and args.device == "cuda":
@@ -111,6 +123,8 @@ def run_reference(args):
     assert os.path.realpath(sparktorch.__file__).startswith(os.path.realpath(ref_dir)), sparktorch.__file__
     n = args.batch * args.gpus
     x, y = synthetic_mnist(n, seed=1)
+    if args.mode == "hogwild":
+        return run_reference_hogwild(args, spark, x, y)
     df = spark.createDataFrame({"label": y, "features": x.astype(np.float64)}, numPartitions=args.gpus)
     if args.model == "cnn":
         from sparktorch_b200.models.mnist import MnistCNN      # plain nn.Module definition (same net as examples/cnn_network.py)
@@ -118,12 +132,8 @@ def run_reference(args):
         net = MnistCNN()
     else:
         net = nn.Sequential(nn.Linear(IN_FEATURES, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, N_CLASSES))
-    obj = serialize_torch_obj(net, nn.CrossEntropyLoss(), TimedAdam, lr=1e-3,
+    obj = serialize_torch_obj(net, LoggedCrossEntropy(), TimedAdam, lr=1e-3,
                               warmup=args.warmup, steps=args.steps, out_dir=out_dir)
-    if args.mode == "hogwild":
-        emit({"impl": "reference", "unavailable": "the reference's hogwild workers ignore `device` (CPU only, Flask server on the "
-              "driver; SURVEY quirk Q10) - no GPU arm exists for it; use --mode synchronous"})
-        return
     est = SparkTorch(inputCol="features", labelCol="label", predictionCol="predictions", torchObj=obj,
                      iters=args.warmup + args.steps + 1, verbose=0, mode="synchronous", device=args.device,
                      miniBatch=-1, earlyStopPatience=-1)
@@ -153,6 +163,82 @@ def run_reference(args):
         "e2e": {"value": n * args.steps / (wall_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 4, "note": "wall clock over the same K iterations; data resident on device"},
         "gpu_launches": 0, "fit_seconds": fit_s,
+        "loss": loss_record(*((recs[0]["loss"]["first"], recs[0]["loss"]["last"]) if recs[0].get("loss") else (None, None))),
+        "clocks": clocks.summary(*clocks.window(min(r["host_t0"] for r in recs), max(r["host_t1"] for r in recs))),
+    })
+    spark.stop()
+
+
+def run_reference_hogwild(args, spark, x, y):
+    """the reference's hogwild workers are CPU-only (hogwild.py:65-142 ignores `device`, the parameter server
+    is a Flask process), so the bar for `mode='hogwild'` on GPUs is its data flow - pull all parameters, forward/backward
+    in torch eager fp32, push all gradients, server-side Adam - carried by NCCL broadcast / reduce per parameter per
+    iteration (baseline/ref_harness.py hogwild_nccl_worker).  One barrier task per GPU on the same local Spark runtime."""
+    import numpy as np
+    import torch
+
+    from sparktorch_b200.utils.clocks import ClockSampler
+
+    n_per = args.batch * 8                      # a few mini-batches per partition, resident on the device like the reference's
+    iters = args.warmup + args.steps
+    x = x[: n_per * args.gpus] if len(x) >= n_per * args.gpus else x
+    model_name = args.model
+    warmup, steps, batch, gpus = args.warmup, args.steps, args.batch, args.gpus
+
+    def task(ctx_index, block):
+        import torch.distributed as dist
+        from pyspark.taskcontext import BarrierTaskContext
+
+        from baseline.ref_harness import hogwild_nccl_worker
+        from sparktorch_b200.util import rows_to_block
+        from sparktorch_b200.parallel import rendezvous
+
+        ctx = BarrierTaskContext.get()
+        dev = torch.device("cuda", ctx.partitionId() % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        rank, world = rendezvous.init_from_barrier(ctx, dev)
+        try:
+            X, Y = rows_to_block(block)
+            torch.manual_seed(0)
+            if model_name == "cnn":
+                from sparktorch_b200.models.mnist import MnistCNN      # plain nn.Module (same net as examples/cnn_network.py)
+
+                net = MnistCNN()
+            else:
+                import torch.nn as nn
+
+                net = nn.Sequential(nn.Linear(IN_FEATURES, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, N_CLASSES))
+            rec = hogwild_nccl_worker(rank, world, dev, net, X.astype(np.float32), Y, iters, warmup, steps, 1e-3, batch)
+        finally:
+            rendezvous.shutdown()
+        return [rec]
+
+    task._accepts_blocks = True
+    from sparktorch_b200.distributed import mapPartitionsWithIndex
+
+    df = spark.createDataFrame({"label": y[: len(x)], "features": x}, numPartitions=gpus)
+    clocks = ClockSampler(int(os.environ.get("SPARKTORCH_CLOCK_PERIOD_MS", "100")), list(range(gpus))).start()
+    t0 = time.time()
+    recs = mapPartitionsWithIndex(df.rdd, task).collect()
+    fit_s = time.time() - t0
+    time.sleep(0.15)
+    clocks.stop()
+    dev_ms = max(r["device_ms"] for r in recs)
+    wall_ms = max(r["wall_ms"] for r in recs)
+    n = batch * gpus
+    emit({
+        "impl": "reference", "metric": METRIC_CNN if model_name == "cnn" else METRIC, "value": n * steps / (dev_ms / 1e3), "unit": "samples/s",
+        "n_gpus": gpus, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"model": MODEL_NAME[model_name], "global_batch": n, "seq_len": IN_FEATURES, "parallelism": f"dp{gpus}",
+                   "per_gpu_batch": batch, "mode": "hogwild", "backend": "nccl",
+                   "note": "BASELINE.md B2: the reference's hogwild loop (pull all params / eager fwd+bwd / push all grads / server-side "
+                           "Adam) with its CPU-only Flask+dill transport replaced by NCCL broadcast+reduce per parameter; rank 0 = server",
+                   "l2": f"{n_per}-row partition resident on the device, random mini-batches"},
+        "e2e": {"value": n * steps / (wall_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                "note": "wall clock over the same K iterations; data resident on device, loss.item() every iteration"},
+        "gpu_launches": 0, "fit_seconds": fit_s,
+        "loss": loss_record(recs[0]["loss"]["first"], recs[0]["loss"]["last"]),
         "clocks": clocks.summary(*clocks.window(min(r["host_t0"] for r in recs), max(r["host_t1"] for r in recs))),
     })
     spark.stop()
@@ -205,6 +291,11 @@ def run_ours(args):
         out["note"] = f"nvidia-smi samples ({period} ms period) taken during the timed window +-0.12 s"
         return out
 
+    def loss_of(hist):
+        tl = [v for v in hist.get("train_loss", []) if v is not None]
+        k = max(1, min(3, len(tl) // 2))
+        return loss_record(sum(tl[:k]) / k, sum(tl[-k:]) / k) if tl else loss_record(None, None)
+
     gb = args.batch * args.gpus
     dev_ms = h["window_ms"]["device_ms"]
     value = gb * args.steps / (dev_ms / 1e3)
@@ -222,6 +313,8 @@ def run_ours(args):
                           f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
                           "weights/optimizer state stay cache resident as in any training loop")},
         "gpu_launches": int(h.get("gpu_launches_per_step", 0) * args.steps),
+        "loss": loss_of(h),
+        "step_kernel": h.get("step_kernel"),
         "clocks": clock_summary(h),
     }
     if he is not None:
@@ -231,9 +324,13 @@ def run_ours(args):
                       "d2h_bytes_per_step": he.get("d2h_bytes_per_step", 0),
                       "ms_per_step": e_ms / args.steps, "engine": he.get("engine"),
                       "gpu_launches": int(he.get("gpu_launches_per_step", 0) * args.steps),
-                      "clocks": clock_summary(he)}
+                      "loss": loss_of(he), "clocks": clock_summary(he)}
     emit(out)
     spark.stop()
+    bad = [k for k, rec in (("value", out["loss"]), ("e2e", out.get("e2e", {}).get("loss"))) if rec is not None and not rec["finite_and_decreasing"]]
+    if bad:
+        sys.stderr.write(f"bench.py: training loss is not finite and decreasing for {bad}: {out['loss']} - the number above is invalid\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@
 
 namespace st {
 
-constexpr int MS_THREADS = 192;
+constexpr int MS_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int MS_STAGES = 8;
 constexpr int MS_MAX_TASKS = 24;          // tasks per CTA per step (descriptor copies live in shared memory)
 constexpr int MS_MAX_FLAGS = 64;          // cross-GPU flag ids; flag word = flags[dst][id * 8 + src_rank]
@@ -30,6 +30,7 @@ enum MsFlags : int32_t {
   MS_LOSS_CE = 1 << 10,
   MS_LOSS_MSE = 1 << 11,
   MS_LBL_WIN = 1 << 12,    // labels / targets are the resident partition's (offset by the window)
+  MS_FUSED_OPT = 1 << 13,  // one GPU: the weight-gradient tile applies the optimizer to its parameters in the epilogue
 };
 
 struct MsWait {            // kind 0: none; 1: local counter (>= epoch * need); 2: cross-GPU flag `idx` from every rank in `mask` (>= epoch)

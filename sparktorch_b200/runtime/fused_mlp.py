@@ -653,7 +653,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     torch.cuda.synchronize(device)
     if mega is not None and int(mega.d_error[0]) != 0:
         raise RuntimeError("K-STEP kernel gave up waiting (code, cta, task, epoch) = %s" % mega.d_error.cpu().tolist())
-    if mega is not None and os.environ.get("SPARKTORCH_MEGA_PROF") and rank == 0:
+    if mega is not None and os.environ.get("SPARKTORCH_MEGA_PROF"):
         import json
 
         stamps = mega_prof.cpu().view(mega.grid_used, 24, 8).tolist()
@@ -663,7 +663,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
             c, j = mega.cta_of_task[ti]
             recs.append({"group": td["group"], "cta": c, "slot": j, "m0": td["m0"], "n0": td["n0"], "t": stamps[c][j],
                          "kb": kbs[c][j][: max(1, min(16, td["num_kb"]))]})
-        with open(os.environ["SPARKTORCH_MEGA_PROF"], "w") as fh:
+        with open(os.environ["SPARKTORCH_MEGA_PROF"] + ("" if rank == 0 else f".rank{rank}"), "w") as fh:
             json.dump({"world": world, "tasks": recs, "info": mega.describe()}, fh)
     t_end = time.time()
     n_done = plan.fu.iters_done()

@@ -34,7 +34,7 @@ MS_MAX_TASKS = 24
 MS_MAX_FLAGS = 64
 MS_GEMM, MS_UPDATE, MS_DECIDE = 1, 2, 3
 F_A_MN, F_B_MN, F_RELU, F_A_WIN, F_B_WIN, F_BIAS, F_MASK = 1, 2, 4, 8, 16, 32, 64
-F_OUT_BF16, F_OUT_F32, F_COLSUM, F_LOSS_CE, F_LOSS_MSE, F_LBL_WIN = 128, 256, 512, 1024, 2048, 4096
+F_OUT_BF16, F_OUT_F32, F_COLSUM, F_LOSS_CE, F_LOSS_MSE, F_LBL_WIN, F_FUSED_OPT = 128, 256, 512, 1024, 2048, 4096, 8192
 
 # mirrors struct MsTask (csrc/mlp_step.h), 256 bytes
 MS_TASK = np.dtype([
@@ -187,7 +187,17 @@ class MegaPlan:
             lo, hi = max(seg_range[sidx][0], self.owned[0]), min(seg_range[sidx][1], self.owned[1])
             return _cdiv(hi - lo, ch) if lo < hi else 0
 
+        # one GPU: Adam/SGD is applied by the weight-gradient tiles themselves (no update phase for the weights)
+        # (opt-in: with thread = weight row the in-place update writes 32-byte pieces of 32 different rows per instruction;
+        #  the separate, fully coalesced update chunks are faster for the MNIST-sized layers - profiles/kstep_timeline_*.md)
+        fused_opt = single and os.environ.get("SPARKTORCH_MEGA_FUSED_OPT", "0") == "1"
+        self.fused_opt = fused_opt
+        wg_tiles = {l: _cdiv(d[l], 128) * _cdiv(d[l - 1], 64) for l in range(1, L + 1)}
+
         def w_pub(sidx: int, early=True):          # "segment sidx as of the previous step is published everywhere"
+            if fused_opt and sidx in seg_of_w:
+                l = seg_of_w.index(sidx) + 1
+                return w_cnt(c_wg(l), wg_tiles[l], lag=1, early=early)
             if single:
                 return w_cnt(c_upd(sidx), my_chunks(sidx), lag=1, early=early)
             return w_flag(f_pub(sidx), 1, seg_owner[sidx], early=early)
@@ -317,24 +327,29 @@ class MegaPlan:
             for mt in range(mtl):
                 for nt in range(ntl):
                     src_rows = self.x_src.shape[0] if l == 1 else B
-                    new_task(type=MS_GEMM, flags=F_A_MN | F_B_MN | F_OUT_F32 | (F_B_WIN if (l == 1 and windowed) else 0),
-                             m0=mt * 128, n0=nt * 64, M=d[l], N=d[l - 1], num_kb=nkb, block_n=64,
+                    new_task(type=MS_GEMM, flags=F_A_MN | F_B_MN | F_OUT_F32 | (F_B_WIN if (l == 1 and windowed) else 0) | (F_FUSED_OPT if fused_opt else 0),
+                             seg=sw, m0=mt * 128, n0=nt * 64, M=d[l], N=d[l - 1], num_kb=nkb, block_n=64,
                              tmap_a=[self._tmap(self.dz[l][p], B, d[l], 64) for p in range(2)],
                              tmap_b=[self._tmap(src_of(l - 1, p), src_rows, d[l - 1], 64) for p in range(2)],
                              out_f32=_addr(fu.grad, w_off_arena[l - 1]), ld_f32=d[l - 1],
-                             wait=[w_cnt(c_dz(l), n_dz_tiles[l])] + ([w_cnt(c_act(l - 1), n_f_tiles[l - 1], early=True)] if l > 1 else []),
+                             wait=[w_cnt(c_dz(l), n_dz_tiles[l])] + ([w_cnt(c_act(l - 1), n_f_tiles[l - 1], early=True)] if l > 1 else [])
+                             # fused optimizer: this tile overwrites W_l, which this step's dgrad B_l still reads until dZ_{l-1} is complete
+                             + ([w_cnt(c_dz(l - 1), _cdiv(B, 128) * _cdiv(d[l - 1], 64))] if (fused_opt and l > 1) else []),
                              sig=[c_wg(l), mtl * ntl, -1 if single else f_gw(l), all_mask],
                              cost=1.5 + 0.15 * nkb, group=f"G{l}")
             # W_l may only be overwritten (on EVERY replica: the owner publishes everywhere) once every replica's dgrad of
             # this step has read it: dZ_{l-1} complete  <=>  the B_l tiles are done
-            w_gw = w_cnt(c_wg(l), mtl * ntl) if single else w_flag(f_gw(l), 0, all_mask)
-            update_tasks(sw, [w_gw] + ([w_dz(l - 1)] if l > 1 else []), 1, 0)
+            if not fused_opt:
+                w_gw = w_cnt(c_wg(l), mtl * ntl) if single else w_flag(f_gw(l), 0, all_mask)
+                update_tasks(sw, [w_gw] + ([w_dz(l - 1)] if l > 1 else []), 1, 0)
         self.task_dicts = tasks
         if not self._place():
             return
         self.ok = True
 
     def _pick_chunk(self, owned_elems: int) -> int:
+        # 256 update threads x two float4 in flight = 2048 floats per pass; one pass per chunk whenever the owned shard
+        # spreads over the grid that way
         c = _pad(_cdiv(max(owned_elems, 1), max(1, self.grid)), 512)
         return int(min(2048, max(512, c)))
 
@@ -359,7 +374,9 @@ class MegaPlan:
                 # program order, which is what keeps the loss partial slots (double buffered) safe to reuse
                 best = next(c for c in range(G) if lists[c] and lists[c][0] == 0)
             else:
-                best = min(range(G), key=lambda c: (max(ready, free[c]), free[c] > ready, c))
+                # earliest start; among equals the CTA with the fewest tasks so far (an idle SM beats queueing behind a finished
+                # task: epilogues are latency bound, a second tile on the same SM would wait for the first one's stores)
+                best = min(range(G), key=lambda c: (max(ready, free[c]), len(lists[c]), c))
             start = max(ready, free[best])
             fin = start + t["cost"]
             free[best] = fin
@@ -514,7 +531,8 @@ class MegaEmulator:
                 for r in range(self.W):
                     if (mask >> r) & 1 and int(fl[idx * 8 + r]) < epoch - need:
                         return False
-        if int(t["type"]) == MS_UPDATE and mp.patience > 0 and (int(self.counters[ri][mp.decide_cnt]) >> 1) < epoch:
+        needs_decision = int(t["type"]) == MS_UPDATE or (int(t["type"]) == MS_GEMM and int(t["flags"]) & F_FUSED_OPT)
+        if needs_decision and mp.patience > 0 and (int(self.counters[ri][mp.decide_cnt]) >> 1) < epoch:
             return False
         return True
 
@@ -528,7 +546,35 @@ class MegaEmulator:
                 if (sm >> r) & 1:
                     self.plans[r].flags[sf * 8 + ri] = epoch
 
-    def _gemm(self, ri: int, t, par: int, win_off: int) -> None:
+    def _fused_opt_tile(self, ri: int, t, grad, m0, n0, rows, cols, step1) -> None:
+        """one GPU: the weight-gradient tile applies the optimizer to the parameters it covers"""
+        from sparktorch_b200.runtime.optim import apply_update_
+
+        mp = self.plans[ri]
+        fu = mp.plan.fu
+        flat, off = self.reg.resolve(int(t["out_f32"]))
+        assert flat.data_ptr() == fu.grad.data_ptr()
+        ld = int(t["ld_f32"])
+        idx = (off + (torch.arange(m0, m0 + rows)[:, None] * ld + torch.arange(n0, n0 + cols)[None, :])).reshape(-1)
+        p = fu.param[idx].clone()
+        st = {}
+        if fu.m is not None:
+            st["m" if mp.spec.kind != "sgd" else "buf"] = fu.m[idx - mp.shard_lo].clone()
+        if fu.v is not None:
+            st["v"] = fu.v[idx - mp.shard_lo].clone()
+        apply_update_(mp.spec, p, grad.reshape(-1).clone(), st, step1)
+        fu.param[idx] = p
+        if fu.m is not None:
+            fu.m[idx - mp.shard_lo] = st["m" if mp.spec.kind != "sgd" else "buf"]
+        if fu.v is not None:
+            fu.v[idx - mp.shard_lo] = st["v"]
+        s_off, _r, s_cols, w_off, w_ld = (int(x) for x in mp.seg_rows[int(t["seg"])][:5])
+        assert s_off == off and s_cols == ld
+        if w_off >= 0:
+            widx = (w_off + (torch.arange(m0, m0 + rows)[:, None] * w_ld + torch.arange(n0, n0 + cols)[None, :])).reshape(-1)
+            fu.wbf16[widx] = p.to(fu.wbf16.dtype)
+
+    def _gemm(self, ri: int, t, par: int, win_off: int, step1: int = 0) -> None:
         mp = self.plans[ri]
         fl, bn, kp = int(t["flags"]), int(t["block_n"]), int(t["num_kb"]) * 64
         m0, n0, M, N = int(t["m0"]), int(t["n0"]), int(t["M"]), int(t["N"])
@@ -567,7 +613,10 @@ class MegaEmulator:
         if fl & F_OUT_BF16:
             out = self.reg.view2d(int(t["out_bf16"][par]), M, N, int(t["ld_out"]))
             out[m0: m0 + rows, n0: n0 + cols] = acc.to(out.dtype)
-        if fl & F_OUT_F32:
+        if fl & F_FUSED_OPT:
+            if not (mp.patience > 0 and int(self.counters[ri][mp.decide_cnt]) & 1):
+                self._fused_opt_tile(ri, t, acc, m0, n0, rows, cols, step1)
+        elif fl & F_OUT_F32:
             out = self.reg.view2d(int(t["out_f32"]), M, N, int(t["ld_f32"]))
             out[m0: m0 + rows, n0: n0 + cols] = acc
         if fl & F_COLSUM:
@@ -658,7 +707,7 @@ class MegaEmulator:
                     continue
                 t = mp.tasks[c, j]
                 epoch = epoch0 + s + 1
-                td = dict(wait=[tuple(int(x) for x in w) for w in t["wait"]], type=int(t["type"]))
+                td = dict(wait=[tuple(int(x) for x in w) for w in t["wait"]], type=int(t["type"]), flags=int(t["flags"]))
                 if not self._waits_ok(ri, td, epoch):
                     continue
                 par = (epoch0 + s) & 1
@@ -666,7 +715,7 @@ class MegaEmulator:
                 win_off = (it % mp.window[0]) * mp.window[1] if mp.window else 0
                 ty = int(t["type"])
                 if ty == MS_GEMM:
-                    self._gemm(ri, t, par, win_off)
+                    self._gemm(ri, t, par, win_off, step0 + s + 1)
                 elif ty == MS_UPDATE:
                     self._update(ri, t, step0 + s + 1)
                 elif ty == MS_DECIDE:

@@ -202,3 +202,40 @@ def test_mnist_dnn_plan_shape():
     info = megas[0].describe()
     assert info["groups"]["F1"] == 16 and info["groups"]["F3"] == 2 and info["groups"]["G1"] == 26 and info["groups"]["D"] == 1
     assert info["ctas"] <= 148 and info["max_tasks_per_cta"] <= 24
+
+
+@pytest.mark.parametrize("flags,fused", [("0", "1"), ("0", "0"), ("1", "1")])
+def test_single_gpu_variants_and_early_stop(monkeypatch, flags, fused):
+    """one GPU: (a) optimizer fused into the weight-gradient tiles, (b) separate update chunks on counters, (c) the flag
+    protocol of the multi-GPU case with one rank - all with early stopping (the stopping step's update is skipped)."""
+    monkeypatch.setenv("SPARKTORCH_MEGA_FLAGS", flags)
+    monkeypatch.setenv("SPARKTORCH_MEGA_FUSED_OPT", fused)
+    torch.manual_seed(7)
+    model = nn.Sequential(nn.Linear(30, 70), nn.ReLU(), nn.Linear(70, 150), nn.ReLU(), nn.Linear(150, 4))
+    B = 140
+    g = torch.Generator().manual_seed(8)
+    data = [(torch.randn(B, 30, generator=g), torch.randint(0, 4, (B,), generator=g))]
+    kw = {"lr": 0.05, "momentum": 0.5, "maximize": True}
+    plans, megas, _ = _ranks(model, nn.CrossEntropyLoss(), torch.optim.SGD, kw, 1, B, patience=3, data=data, grid=9)
+    assert megas[0].fused_opt == (flags == "0" and fused == "1")
+    emu = MegaEmulator(megas)
+    emu.run(10, seed=3)
+    from sparktorch_b200.early_stopper import EarlyStopping
+
+    ref = copy.deepcopy(model)
+    opt = torch.optim.SGD(ref.parameters(), **kw)
+    es = EarlyStopping(patience=3)
+    losses = []
+    for _ in range(10):
+        opt.zero_grad()
+        loss = nn.CrossEntropyLoss()(ref(data[0][0]), data[0][1])
+        loss.backward()
+        losses.append(float(loss.detach()))
+        if es.step(losses[-1]):
+            break
+        opt.step()
+    assert len(losses) < 10
+    st = emu.state[0]
+    assert st["stopped"] and st["iter"] == len(losses) and st["step"] == len(losses) - 1
+    np.testing.assert_allclose(st["losses"], losses, rtol=1e-4)
+    _check(plans, ref)
