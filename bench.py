@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--model", default="dnn", choices=["dnn", "cnn"], help="dnn: examples/simple_dnn.py, cnn: examples/simple_cnn.py")
+    ap.add_argument("--model", default="dnn", choices=["dnn", "cnn", "resnet50"],
+                    help="dnn: examples/simple_dnn.py, cnn: examples/simple_cnn.py, resnet50: BASELINE config 4 (bench/resnet50_bench.py)")
     ap.add_argument("--mode", default="synchronous", choices=["synchronous", "hogwild"])
     a = ap.parse_args()
     if a.model == "cnn" and "--batch" not in sys.argv:
@@ -216,10 +217,13 @@ def run_reference_hogwild(args, spark, x, y):
     task._accepts_blocks = True
     from sparktorch_b200.distributed import mapPartitionsWithIndex
 
+    from sparktorch_b200.torch_distributed import handle_data
+
     df = spark.createDataFrame({"label": y[: len(x)], "features": x}, numPartitions=gpus)
+    rdd = df.rdd.mapPartitions(handle_data("features", "label"))
     clocks = ClockSampler(int(os.environ.get("SPARKTORCH_CLOCK_PERIOD_MS", "100")), list(range(gpus))).start()
     t0 = time.time()
-    recs = mapPartitionsWithIndex(df.rdd, task).collect()
+    recs = mapPartitionsWithIndex(rdd, task).collect()
     fit_s = time.time() - t0
     time.sleep(0.15)
     clocks.stop()
@@ -333,9 +337,51 @@ def run_ours(args):
         sys.exit(3)
 
 
+def run_resnet50(args):
+    """BASELINE.json config 4 (ResNet-50, lazy envelope, synthetic 3x224x224 rows) - delegated to bench/resnet50_bench.py, whose
+    JSON line is completed with the keys of the bench contract.  Ours runs the bf16 fused plan (runtime/fused_resnet.py; the
+    block-scaled fp8 operand path of that config is NOT implemented - DESIGN.md section 8), the reference arm its unmodified fp32 loop."""
+    import io
+    from contextlib import redirect_stdout
+    from types import SimpleNamespace
+
+    sys.path.insert(0, os.path.join(ROOT, "bench"))
+    import resnet50_bench as rb
+
+    batch = args.batch if "--batch" in sys.argv else 32
+    a = SimpleNamespace(gpus=args.gpus, steps=args.steps, warmup=max(3, args.warmup), batch=batch, image=224, engine="fused",
+                        device=args.device, impl=args.impl)
+    buf = io.StringIO()
+    argv = sys.argv
+    try:
+        sys.argv = [argv[0], "--gpus", str(a.gpus), "--steps", str(a.steps), "--warmup", str(a.warmup), "--batch", str(a.batch),
+                    "--impl", a.impl, "--device", a.device]
+        with redirect_stdout(buf):
+            rb.main()
+    finally:
+        sys.argv = argv
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    if not lines:
+        emit({"impl": args.impl, "unavailable": "resnet50 run produced no result: " + buf.getvalue()[-300:].replace("\n", " ")})
+        return
+    d = json.loads(lines[-1])
+    emit({"impl": args.impl, "metric": "ResNet-50 samples/sec (whole job, device-timed, max over ranks)", "value": d["value"],
+          "unit": "samples/s", "n_gpus": args.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": d["ms_per_step"],
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "fp32" if args.impl == "reference" else "bf16", "data": "synthetic",
+          "config": {"model": "ResNet-50 (lazy envelope) SGD(lr=0.1, momentum=0.9) CE, 3x224x224", "global_batch": d["global_batch"],
+                     "seq_len": 3 * 224 * 224, "parallelism": f"dp{args.gpus}", "per_gpu_batch": a.batch, "mode": "synchronous",
+                     "engine": d.get("engine"), "comm": d.get("comm"),
+                     "note": "bf16 fused plan; block-scaled fp8 (BASELINE config 4's precision) is not implemented",
+                     "l2": "activations of a 32 x 3 x 224 x 224 batch exceed L2 several times over"},
+          "gpu_launches": int((d.get("gpu_launches_per_step") or 0) * a.steps)})
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.model == "resnet50":
+        run_resnet50(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -72,12 +72,6 @@ ST_DEVINL void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int3
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-ST_DEVINL void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 ST_DEVINL void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

@@ -26,6 +26,8 @@
 // `elect.sync` picks the issuing lane) - from a `lane == 0` branch every one of them is wrapped in an
 // R2UR waterfall loop; and the code must stay small - 300 KB of fully unrolled epilogues missed the
 // instruction cache on every task.  Hence the rolled 8-column epilogue below.
+#include <cstddef>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "mlp_step.h"
@@ -121,12 +123,13 @@ struct MsShared {
   uint64_t tmem_empty_bar[2];
   uint32_t tmem_ptr;
   uint32_t stop;            // early-stop decision of the current step (update tasks)
-  float loss;               // loss partial of the current tile
-  float pad0;
+  uint32_t pad_[2];         // (keeps bias / colsum 16-byte aligned for the vector loads of the lean epilogues)
+  float loss_w[4];          // loss partial of the current tile, one slot per epilogue warp of the first group
   float bias[64];
-  float colsum[64];
+  float colsum[4][64];      // column sums of the current tile per TMEM lane quadrant (summed in a fixed order: run-to-run bit-exact)
 };
 static_assert(sizeof(MsShared) <= MS_MISC_BYTES, "misc region");
+static_assert(offsetof(MsShared, bias) % 16 == 0 && offsetof(MsShared, colsum) % 16 == 0, "vector loads");
 
 // a wait that never ends is a hang of every GPU of the job: give up loudly
 __device__ __noinline__ void ms_timeout(uint32_t* error, int code, int task, uint32_t epoch) {
@@ -506,7 +509,7 @@ __device__ __noinline__ void ms_epilogue_rolled(const MsTask* t, MsShared* sh, c
       }
       v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
       v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
-      if (lane < 8) atomicAdd(&sh->colsum[c_begin + c0 + lane], v1);
+      if (lane < 8) sh->colsum[q][c_begin + c0 + lane] = v1;
     }
   }
 }
@@ -517,7 +520,7 @@ __device__ __noinline__ void ms_epilogue_rolled(const MsTask* t, MsShared* sh, c
 // of the next 8 columns is issued before the current ones are processed.
 template <bool BIAS, bool RELU, bool MASK, bool COLSUM>
 ST_DEVINL void ms_epi_bf16_lean(const MsTask* t, MsShared* sh, int par, uint32_t tacc, int row, bool row_ok, int lane,
-                                int c_begin, int ncols, uint64_t* tmem_empty) {
+                                int c_begin, int ncols, uint64_t* tmem_empty, int q) {
   const int n0 = t->n0 + c_begin;
   __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(t->out_bf16[par]) + size_t(row) * t->ld_out + n0;
   const __nv_bfloat16* mrow = nullptr;
@@ -594,7 +597,7 @@ ST_DEVINL void ms_epi_bf16_lean(const MsTask* t, MsShared* sh, int par, uint32_t
       }
       v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
       v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
-      if (lane < 8) atomicAdd(&sh->colsum[c_begin + c0 + lane], v1);
+      if (lane < 8) sh->colsum[q][c_begin + c0 + lane] = v1;
     }
   }
 }
@@ -701,13 +704,13 @@ ST_DEVINL bool ms_epilogue_lean(const MsTask* t, MsShared* sh, const MsParams& p
   }
   const int sel = ((flags & MS_BIAS) ? 1 : 0) | ((flags & MS_RELU) ? 2 : 0) | ((flags & MS_MASK) ? 4 : 0) | ((flags & MS_COLSUM) ? 8 : 0);
   switch (sel) {
-    case 0: ms_epi_bf16_lean<false, false, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 1: ms_epi_bf16_lean<true, false, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 2: ms_epi_bf16_lean<false, true, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 3: ms_epi_bf16_lean<true, true, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 4: ms_epi_bf16_lean<false, false, true, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 8: ms_epi_bf16_lean<false, false, false, true>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
-    case 12: ms_epi_bf16_lean<false, false, true, true>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty); break;
+    case 0: ms_epi_bf16_lean<false, false, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 1: ms_epi_bf16_lean<true, false, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 2: ms_epi_bf16_lean<false, true, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 3: ms_epi_bf16_lean<true, true, false, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 4: ms_epi_bf16_lean<false, false, true, false>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 8: ms_epi_bf16_lean<false, false, false, true>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
+    case 12: ms_epi_bf16_lean<false, false, true, true>(t, sh, par, tacc, row, row_ok, lane, c_begin, ncols, tmem_empty, q); break;
     default: return false;                          // (never reached for the tasks mega_mlp.py builds; keeps the contract honest)
   }
   return true;
@@ -777,7 +780,7 @@ ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-  if (lane == 0) atomicAdd(&sh->loss, li * t->loss_scale);
+  if (lane == 0) sh->loss_w[q] = li * t->loss_scale;
   // dZ_L (bf16): whole 8-column groups up to the pitch (a multiple of 8); columns >= N inside them are written as zeros
   if (row_ok) {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(t->out_bf16[par]) + size_t(row) * t->ld_out;
@@ -807,7 +810,7 @@ ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p
       }
     }
     if constexpr (NC == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-    if (lane < NC) atomicAdd(&sh->colsum[lane], v[0]);
+    if (lane < NC) sh->colsum[q][lane] = v[0];
   }
 }
 
@@ -853,10 +856,8 @@ ST_DEVINL void ms_update_chunk(const MsTask* t, const MsParams& p, const MsPeerT
   }
 }
 
-ST_DEVINL void ms_decide(const MsTask* t, const MsParams& p, const MsPeerTable* peers, uint32_t epoch, int par, int64_t it) {
-  float loss = 0.f;
-  for (int r = 0; r < p.world; ++r)
-    for (int k = 0; k < p.n_mt; ++k) loss += ld_relaxed_sys_f32(peers->grad[r] + p.loss_off + int64_t(par) * p.n_mt + k);
+// `loss` = the replicas' loss partials summed in (rank, m-tile) order, gathered by the whole warp (see the call site)
+ST_DEVINL void ms_decide(const MsTask* t, const MsParams& p, const MsPeerTable* peers, uint32_t epoch, int64_t it, float loss) {
   loss /= float(p.world);
   StepState* st = p.state;
   int stop_now = 0;
@@ -936,8 +937,12 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
     const uint4* ps = reinterpret_cast<const uint4*>(p.peers);
     uint4* pd = reinterpret_cast<uint4*>(peers);
     for (int i = threadIdx.x; i < int(sizeof(MsPeerTable) / 16); i += MS_THREADS) pd[i] = ps[i];
-    if (threadIdx.x < 64) { sh->bias[threadIdx.x] = 0.f; sh->colsum[threadIdx.x] = 0.f; }
-    if (threadIdx.x == 0) { sh->loss = 0.f; sh->stop = 0; }
+    if (threadIdx.x < 64) {
+      sh->bias[threadIdx.x] = 0.f;
+      for (int k = 0; k < 4; ++k) sh->colsum[k][threadIdx.x] = 0.f;
+    }
+    if (threadIdx.x < 4) sh->loss_w[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) sh->stop = 0;
   }
   tc_fence_before();
   __syncthreads();
@@ -1111,13 +1116,11 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           if (flags & (MS_COLSUM | MS_LOSS_CE | MS_LOSS_MSE)) {
             asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");
             if ((flags & MS_COLSUM) && et < bn) {
-              if (n0 + et < N) reinterpret_cast<float*>(t->colsum)[n0 + et] = sh->colsum[et];
-              sh->colsum[et] = 0.f;
+              if (n0 + et < N)
+                reinterpret_cast<float*>(t->colsum)[n0 + et] = ((sh->colsum[0][et] + sh->colsum[1][et]) + sh->colsum[2][et]) + sh->colsum[3][et];
             }
-            if ((flags & (MS_LOSS_CE | MS_LOSS_MSE)) && et == 0) {
-              *reinterpret_cast<float*>(t->loss_slot[par]) = sh->loss;
-              sh->loss = 0.f;
-            }
+            if ((flags & (MS_LOSS_CE | MS_LOSS_MSE)) && et == 0)
+              *reinterpret_cast<float*>(t->loss_slot[par]) = ((sh->loss_w[0] + sh->loss_w[1]) + sh->loss_w[2]) + sh->loss_w[3];
           }
           if (stamp && et == 0) prof[ti * 8 + 6] = (long long)globaltimer_ns();
           asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");      // every store of the tile has been issued by its thread
@@ -1145,8 +1148,19 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           if (warp == 2) {
             if (stamp && lane == 0) prof[ti * 8 + 0] = (long long)globaltimer_ns();
             ms_wait_warp(t, ti, p, epoch, lane, -1);
+            // all W x n_mt loss partials are fetched at once (one NVLink round trip instead of W x n_mt in a row: the decision
+            // sits in front of the next step's first forward tile), then summed in a fixed order so every rank gets the same bits
+            float loss = 0.f;
+            const int n_val = p.world * p.n_mt;
+            for (int base = 0; base < n_val; base += 32) {
+              const int i = base + lane;
+              float v = 0.f;
+              if (i < n_val) v = ld_relaxed_sys_f32(peers->grad[i / p.n_mt] + p.loss_off + int64_t(par) * p.n_mt + (i % p.n_mt));
+              const int cnt = min(32, n_val - base);
+              for (int j = 0; j < cnt; ++j) loss += __shfl_sync(0xffffffffu, v, j);
+            }
             if (lane == 0) {
-              ms_decide(t, p, peers, epoch, par, it);
+              ms_decide(t, p, peers, epoch, it, loss);
               if (stamp) prof[ti * 8 + 7] = (long long)globaltimer_ns();
             }
             __syncwarp();

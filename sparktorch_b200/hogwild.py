@@ -189,12 +189,12 @@ def handle_model_gpu(index, data, torch_obj, iters=1000, verbose=1, early_stop_p
         cfg = TrainConfig(iters=iters, mini_batch=mini_batch, validation_pct=validation_pct,
                           early_stop_patience=early_stop_patience, verbose=verbose, device=str(dev), seed=seed,
                           time_window=tuple(time_window) if time_window else None, sampling=sampling)
-        res = None
-        if not acquire_lock:      # lock-free: the graph-captured worker with K-AG forward GEMMs
-            from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
+        # the graph-captured worker with K-AG forward GEMMs - with acquireLock (the default) its remote-apply push takes the
+        # owners' stripe locks, without it the push is lock-free; models that do not lower fall through to the eager worker
+        from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
 
-            res = train_partition_hogwild_fused(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params,
-                                                X, Y, cfg, dev, window_len)
+        res = train_partition_hogwild_fused(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params,
+                                            X, Y, cfg, dev, window_len, acquire_lock=acquire_lock)
         if res is None:
             res = train_partition_hogwild(rank, world, raw.model, raw.criterion, raw.optimizer, raw.optimizer_params, X, Y,
                                           cfg, dev, acquire_lock, window_len)

@@ -24,6 +24,26 @@ from sparktorch_b200.runtime.optim import parse_optimizer
 from sparktorch_b200.util import split_validation
 
 
+def compensate_asynchrony(spec, world: int):
+    """W asynchronous workers that apply W optimizer steps per round on gradients taken at (almost) the same stale
+    parameters behave like ONE worker with extra momentum: the implicit momentum of asynchrony is 1 - 1/W (Mitliagkas et
+    al., "Asynchrony begets momentum").  Stacked on Adam's beta1 = 0.9 (or SGD momentum) that is an effective momentum of
+    ~0.99 at 8 workers and training at the reference's learning rates oscillates and diverges (profiles/mgc_n8.log of
+    round 1: the loss falls for ~20 iterations, then climbs above ln 10).  The remote-apply push therefore runs with the
+    explicit momentum reduced so that the TOTAL stays what the user asked for:  1 - beta' = min(1, W (1 - beta)).
+    SPARKTORCH_HOGWILD_COMPENSATE=0 keeps the raw coefficients (the reference's behaviour)."""
+    import dataclasses
+    import os
+
+    if world <= 1 or os.environ.get("SPARKTORCH_HOGWILD_COMPENSATE", "1") != "1":
+        return spec
+    if spec.kind in ("adam", "adamw"):
+        return dataclasses.replace(spec, beta1=1.0 - min(1.0, world * (1.0 - spec.beta1)))
+    if spec.kind == "sgd" and spec.momentum:
+        return dataclasses.replace(spec, momentum=max(0.0, 1.0 - min(1.0, world * (1.0 - spec.momentum))))
+    return spec
+
+
 def pick_stripes(numel: int, world: int, max_stripes: int) -> int:
     per = (numel // 4 + world - 1) // world
     return int(max(1, min(max_stripes, per // 2048)))
@@ -33,7 +53,7 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
                             X: np.ndarray, Y: Optional[np.ndarray], cfg: TrainConfig, device: torch.device,
                             acquire_lock: bool, window_len: int) -> FitResult:
     C = native.load(required=True)
-    spec = parse_optimizer(opt_cls, opt_params)
+    spec = compensate_asynchrony(parse_optimizer(opt_cls, opt_params), world)
     if spec.kind == "other":
         raise RuntimeError("GPU hogwild supports SGD/Adam/AdamW; other optimizers use the HTTP parameter server")
     t_start = time.time()
@@ -59,6 +79,10 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
     model = model.to(device).train()
     if hasattr(criterion, "to"):
         criterion = criterion.to(device)
+    # any module: Linear / Conv2d / CE / MSE on our kernels (ops/module_swap.py) - no library GEMM on the worker's step
+    from sparktorch_b200.ops.module_swap import invalidate_weight_caches, swap_modules
+
+    model, criterion, swap_report = swap_modules(model, criterion, precision=cfg.precision)
     numel = FlatArena.measure(model)
     blk = SymmBlock(device, world, rank)
     blk.reserve("param", numel * 4)
@@ -103,6 +127,7 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
         else:
             xb, yb = x_all, y_all
         worker.pull()                              # P2P all-gather of the owners' shards
+        invalidate_weight_caches()                 # (the pulled snapshot replaced the weights behind the bf16 operand copies)
         loss = step.run(xb, yb)
         loss_in[0] = loss
         if x_val is not None:
@@ -126,7 +151,7 @@ def train_partition_hogwild(rank: int, world: int, model: nn.Module, criterion, 
     t_end = time.time()
     ctrl0 = blk.view("ctrl", torch.int32, C.hw_ctrl_words())
     history = {
-        "engine": "eager", "comm": "HogwildP2P" + ("+locks" if acquire_lock else ""), "world_size": world,
+        "engine": "eager", "kernel_swap": swap_report, "comm": "HogwildP2P" + ("+locks" if acquire_lock else ""), "world_size": world,
         "train_loss": loss_hist[:done].cpu().tolist(), "stopped_at": stopped_at, "iters_run": done,
         "samples_per_step": (cfg.mini_batch if use_mb else n), "stripes": stripes,
         "pushes_total": int(ctrl0[2 * C.hw_max_stripes() + 1]) if rank == 0 else None,
@@ -188,14 +213,17 @@ class HogwildBackend:
 
 
 def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg: TrainConfig, device,
-                                  window_len: int):
+                                  window_len: int, acquire_lock: bool = False):
     """Lock-free hogwild for lowered MLPs: the whole worker iteration is one CUDA graph -
     K-AG forward GEMMs (weights gathered from their owners inside the GEMM), fused loss, backward GEMMs,
-    remote-apply push - replayed by the native runner without Python or barriers.  Returns None when the
-    model does not lower (caller falls back to the eager hogwild worker)."""
+    remote-apply push - replayed by the native runner without Python or barriers.  ``acquire_lock`` (the reference's default,
+    torch_distributed.py:189): the push applies every stripe under its owner's spin lock, so concurrent updates of a stripe
+    are serialised like the server's POST /update; the K-AG gather stays a wait-free read (it may see elements of two
+    consecutive versions of a stripe - each element itself is never torn).  Returns None when the model does not lower
+    (caller falls back to the eager hogwild worker, whose GEMMs run on our kernels through ops/module_swap.py)."""
     from sparktorch_b200.runtime.fused_mlp import FusedMLP, _pad, _to_bf16_padded, loss_kind, lower_mlp
 
-    spec = parse_optimizer(opt_cls, opt_params)
+    spec = compensate_asynchrony(parse_optimizer(opt_cls, opt_params), world)
     if spec.kind == "other" or cfg.precision not in ("auto", "bf16"):
         return None
     lowered = lower_mlp(model)
@@ -224,7 +252,7 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
         factory = lambda numel, wb: HogwildBackend(numel, wb, spec, world, rank, device, cfg.early_stop_patience,  # noqa: E731
-                                                   window_len, cfg.iters + 1, False)
+                                                   window_len, cfg.iters + 1, bool(acquire_lock))
         if is_cnn:
             plan = FusedCNN(model, lowered, kind, spec, world, rank, device, Bt, 0, cfg.early_stop_patience, cfg.iters + 1,
                             seed=0 if cfg.seed is None else int(cfg.seed), backend_factory=factory)
@@ -306,7 +334,8 @@ def train_partition_hogwild_fused(rank, world, model, criterion, opt_cls, opt_pa
     t_end = time.time()
     done = be.iters_done()
     history = {
-        "engine": "fused_cnn" if is_cnn else "fused_mlp", "comm": "HogwildP2P+K-AG", "world_size": world, "precision": "bf16",
+        "engine": "fused_cnn" if is_cnn else "fused_mlp", "comm": "HogwildP2P+K-AG" + ("+locks" if acquire_lock else ""),
+        "world_size": world, "precision": "bf16",
         "window_ms": window.result_ms(),
         "train_loss": be.loss_hist[:done].cpu().tolist(), "stopped_at": (done - 1) if be.stopped() else None,
         "iters_run": done, "samples_per_step": Bt, "stripes": be.stripes, "gpu_launches_per_step": plan.n_launch,

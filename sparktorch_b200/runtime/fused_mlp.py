@@ -376,9 +376,10 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         return None
     if getattr(cfg, "comm", "auto") not in ("auto", "p2p"):
         return None                     # an explicit collective (NCCL/gloo oracle) exchange was requested
-    if cfg.checkpoint_dir and (cfg.checkpoint_every > 0 or cfg.resume):
-        # mid-training checkpoints / resume are implemented by the eager engine (same K-AR update kernel, its optimizer
-        # shard and step state are exported); the graph-replay loop has no checkpoint hook yet
+    want_ckpt = bool(cfg.checkpoint_dir and (cfg.checkpoint_every > 0 or cfg.resume))
+    if want_ckpt and os.environ.get("SPARKTORCH_MEGA", "1") != "1":
+        # mid-training checkpoints / resume on the fused path are a feature of the K-STEP loop (below); without it the
+        # eager engine (same update kernel, its optimizer shard and step state are exported) takes over
         return None
     spec = parse_optimizer(opt_cls, opt_params)
     if spec.kind == "other" or world > 8:
@@ -509,7 +510,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                 mx, mt_, mwin = src, tgt_src, None
             mp = MegaPlan(plan, spec, cfg.early_stop_patience, per * rank, owned, mwin, mx, mt_, flag_view, peers=peers,
                           grid=int(os.environ.get("SPARKTORCH_MEGA_GRID", "148")))
-            if mp.ok:
+            if mp.ok and not (want_ckpt and (streaming or gathered)):
                 mega = mp
                 mega_step = mp.materialize()
                 if os.environ.get("SPARKTORCH_MEGA_PROF"):      # per-task globaltimer stamps of the last step of a launch
@@ -517,6 +518,9 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                     mega_step.set_prof(mega_prof)
                     mega_prof_kb = torch.zeros(mp.grid_used * 24 * 64, dtype=torch.int64, device=device)
                     mega_step.set_prof_kb(mega_prof_kb)
+
+        if want_ckpt and mega is None:
+            return None       # (CNN / ResNet plans, validation splits, host-side sampling: the eager engine checkpoints those)
 
         def enqueue_step():
             plan.n_launch = 0
@@ -610,10 +614,45 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         steps_per_launch = int(os.environ.get("SPARKTORCH_MEGA_STEPS", "8" if cfg.early_stop_patience > 0 else "64"))
         t_loop = time.time()
         done = 0
-        segments = [(0, cfg.iters)]
+        start_iter = 0
+        if want_ckpt:
+            from sparktorch_b200.utils import checkpoint as ckpt
+
+            if cfg.resume:
+                # the ranks agree on the newest iteration every one of them holds (utils/checkpoint.py); the step kernel takes
+                # its iteration / optimizer-step numbers as launch parameters, its dependency counters start fresh
+                gens = {it: pl for it, pl in ckpt.load_generations(cfg.checkpoint_dir, rank).items()
+                        if pl.get("numel") == plan.fu.numel and pl.get("engine") == "kstep" and pl.get("world") == world}
+                common = ckpt.agree_on_iteration(sorted(gens), world, device)
+                if common > 0:
+                    sv = gens[common]
+                    fu = plan.fu
+                    fu.param.copy_(sv["param"].to(device))
+                    for dst, key in ((fu.m, "m"), (fu.v, "v")):
+                        if dst is not None and sv.get(key) is not None:
+                            dst.copy_(sv[key].to(device))
+                    fu.state.copy_(sv["state"].to(device))
+                    fu.state[11] = 0                      # StepState.pad[0]: steps since the counters were zeroed
+                    nh = min(fu.loss_hist.numel(), sv["loss_hist"].numel())
+                    fu.loss_hist[:nh].copy_(sv["loss_hist"][:nh].to(device))
+                    fu.mailbox[1] = int(common)
+                    fu.updater.publish()                  # bf16 operand copies of the restored weights
+                    stream.synchronize()
+                    start_iter = int(common)
+                if world > 1:
+                    dist.barrier()
+        segments = [(start_iter, cfg.iters)]
         if cfg.time_window is not None:
             w0, wk = cfg.time_window
             segments = [(0, w0), (w0, w0 + wk), (w0 + wk, cfg.iters)]
+        if want_ckpt and cfg.checkpoint_every > 0:          # cut every segment at the checkpoint boundaries
+            cut = []
+            for lo, hi in segments:
+                while lo < hi:
+                    nxt = min(hi, (lo // cfg.checkpoint_every + 1) * cfg.checkpoint_every)
+                    cut.append((lo, nxt))
+                    lo = nxt
+            segments = cut
         printed = 0
         from sparktorch_b200.utils.watchdog import ProgressWatchdog
 
@@ -629,7 +668,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                     window.before_step(lo)
                 if cfg.verbose:
                     for i in range(lo, hi):
-                        got = (mega_step.run_many(i, i, i, 1, 1, mail_ptr) if (mega is not None and not mega_graph)
+                        got = (mega_step.run_many(i, i, i - start_iter, 1, 1, mail_ptr) if (mega is not None and not mega_graph)
                                else runner.run(i, 1, mail_ptr, 1))
                         stream.synchronize()
                         done += got
@@ -640,13 +679,25 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                 elif mega is not None and not mega_graph:
                     # steps_per_launch whole steps per kernel launch; the kernel itself idles through the rest of a launch
                     # once the stop is latched, the host looks at the mailbox between launches
-                    done += mega_step.run_many(lo, lo, lo, hi - lo, steps_per_launch, mail_ptr if check else 0)
+                    done += mega_step.run_many(lo, lo, lo - start_iter, hi - lo, steps_per_launch, mail_ptr if check else 0)
                 else:
                     done += runner.run(lo, hi - lo, mail_ptr, check)
                 if timed:
                     window.after_step(hi - 1)
                 if plan.fu.stopped():
                     break
+                if want_ckpt and cfg.checkpoint_every > 0 and hi % cfg.checkpoint_every == 0:
+                    stream.synchronize()
+                    fu = plan.fu
+                    ckpt.save(cfg.checkpoint_dir, rank, {
+                        "engine": "kstep", "world": world, "numel": fu.numel, "iters_done": hi, "param": fu.param.cpu(),
+                        "m": None if fu.m is None else fu.m.cpu(), "v": None if fu.v is None else fu.v.cpu(),
+                        "state": fu.state.cpu(), "loss_hist": fu.loss_hist.cpu()})
+                    _inject = os.environ.get("SPARKTORCH_FAULT_INJECT")
+                    if _inject:
+                        from sparktorch_b200.runtime.engine import _maybe_inject_fault
+
+                        _maybe_inject_fault(cfg, rank, hi)
             stream.synchronize()
         finally:
             wd.__exit__()
@@ -677,6 +728,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
         "comm": ("P2PPush" if getattr(plan.fu, "exchange", "") == "push" else "P2PFused" + ("+NVLS" if plan.fu.use_multicast else "")),
         "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,
+        "resumed_from": start_iter,
         "samples_per_step": Bt * world, "loop_seconds": t_end - t_loop, "total_seconds": t_end - t_start,
         "window_ms": window.result_ms(), "gpu_launches_per_step": launches, "graph_nodes": runner.num_nodes() if (mega is None or mega_graph) else 0,
         "streaming": streaming, "sampling": ("stream" if streaming else sampling) if use_mb else "full-batch",

@@ -136,30 +136,32 @@ def main():
     from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild
 
     for lock in (True, False):
-        cfg = TrainConfig(iters=60, mini_batch=128, device="cuda", seed=9)
+        cfg = TrainConfig(iters=120, mini_batch=128, device="cuda", seed=9)
         # W asynchronous workers apply W optimizer steps per "iteration": keep the effective step size constant
         hw = train_partition_hogwild(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam,
                                      {"lr": 2e-3 / world}, X, Y, cfg, dev, acquire_lock=lock, window_len=world)
         hh = hw.history
-        assert np.isfinite(hh["train_loss"]).all() and np.mean(hh["train_loss"][-8:]) < (0.8 if world <= 2 else 0.97) * np.mean(hh["train_loss"][:3]), hh["train_loss"][::10]
+        # asynchronous workers must LEARN at every world size (no per-world thresholds): final loss < 0.7 x initial
+        assert np.isfinite(hh["train_loss"]).all() and np.mean(hh["train_loss"][-8:]) < 0.7 * np.mean(hh["train_loss"][:3]), hh["train_loss"][::10]
         if rank == 0:
-            assert hh["pushes_total"] == 60 * world, hh["pushes_total"]
+            assert hh["pushes_total"] == 120 * world, hh["pushes_total"]
             assert all(torch.isfinite(v).all() for v in hw.state_dict.values())
             print(f"hogwild lock={lock} ok: pushes={hh['pushes_total']} stripes={hh['stripes']} loss {hh['train_loss'][0]:.3f}->{hh['train_loss'][-1]:.3f}", flush=True)
         dist.barrier()
     from sparktorch_b200.parallel.hogwild_p2p import train_partition_hogwild_fused
 
-    cfg = TrainConfig(iters=200, mini_batch=256, device="cuda", seed=9, sampling="sweep")
-    hf = train_partition_hogwild_fused(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam,
-                                       {"lr": 2e-3 / world}, X, Y, cfg, dev, window_len=world)
-    assert hf is not None and hf.history["iters_run"] == 200
-    tl = hf.history["train_loss"]
-    assert np.isfinite(tl).all() and np.mean(tl[-10:]) < (0.7 if world <= 2 else 0.95) * np.mean(tl[:3]), tl[::20]
-    if rank == 0:
-        assert hf.history["pushes_total"] == 200 * world
-        print(f"fused hogwild (K-AG) ok: {tl[0]:.3f}->{tl[-1]:.3f} launches/step {hf.history['gpu_launches_per_step']} "
-              f"{1e6 * hf.history['loop_seconds'] / 200:.1f} us/iter", flush=True)
-    dist.barrier()
+    for lock in (True, False):           # acquireLock=True is the reference's default: it runs the fused K-AG worker as well
+        cfg = TrainConfig(iters=200, mini_batch=256, device="cuda", seed=9, sampling="sweep")
+        hf = train_partition_hogwild_fused(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam,
+                                           {"lr": 2e-3 / world}, X, Y, cfg, dev, window_len=world, acquire_lock=lock)
+        assert hf is not None and hf.history["iters_run"] == 200
+        tl = hf.history["train_loss"]
+        assert np.isfinite(tl).all() and np.mean(tl[-10:]) < 0.7 * np.mean(tl[:3]), tl[::20]
+        if rank == 0:
+            assert hf.history["pushes_total"] == 200 * world
+            print(f"fused hogwild (K-AG, lock={lock}) ok: {tl[0]:.3f}->{tl[-1]:.3f} launches/step {hf.history['gpu_launches_per_step']} "
+                  f"{1e6 * hf.history['loop_seconds'] / 200:.1f} us/iter comm {hf.history['comm']}", flush=True)
+        dist.barrier()
     if rank == 0:
         print("fused fit ok:", [round(v, 3) for v in h["train_loss"][::20]], "comm", h["comm"], flush=True)
         print("MULTI_GPU_OK", flush=True)

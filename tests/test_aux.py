@@ -221,3 +221,41 @@ def test_resume_picks_the_newest_iteration_every_rank_holds(tmp_path):
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_resume_worker, args=(2, port, d, out), nprocs=2, join=True)
     assert dict(out) == {0: 8, 1: 8}
+
+
+def test_asynchrony_compensation_keeps_the_total_momentum():
+    import torch
+
+    from sparktorch_b200.parallel.hogwild_p2p import compensate_asynchrony
+    from sparktorch_b200.runtime.optim import parse_optimizer
+
+    adam = parse_optimizer(torch.optim.Adam, {"lr": 1e-3})
+    assert compensate_asynchrony(adam, 1) is adam
+    assert abs(compensate_asynchrony(adam, 2).beta1 - 0.8) < 1e-9          # 1 - beta' = W (1 - beta)
+    assert abs(compensate_asynchrony(adam, 8).beta1 - 0.2) < 1e-9
+    assert compensate_asynchrony(adam, 16).beta1 == 0.0                     # clipped: asynchrony alone is already more momentum
+    sgd = parse_optimizer(torch.optim.SGD, {"lr": 0.1, "momentum": 0.9})
+    assert abs(compensate_asynchrony(sgd, 4).momentum - 0.6) < 1e-9
+    plain = parse_optimizer(torch.optim.SGD, {"lr": 0.1})
+    assert compensate_asynchrony(plain, 8).momentum == 0.0
+
+
+def test_module_swap_is_a_no_op_without_the_native_extension_or_in_fp32():
+    import torch
+    import torch.nn as nn
+
+    from sparktorch_b200.ops.module_swap import swap_modules, unswap_modules
+
+    net = nn.Sequential(nn.Linear(4, 3), nn.Tanh(), nn.Linear(3, 2))
+    x = torch.randn(5, 4)
+    want = net(x)
+    _, crit, rep = swap_modules(net, nn.CrossEntropyLoss(), precision="fp32")
+    assert rep["disabled"] == "precision=fp32" and rep["linear"] == 0 and len(rep["library_gemm_modules"]) == 2
+    assert isinstance(crit, nn.CrossEntropyLoss)
+    net2, crit2, rep2 = swap_modules(net, nn.CrossEntropyLoss())             # CPU box: extension present, tensors on the CPU
+    torch.testing.assert_close(net2(x), want)                                # CPU inputs take the stock path
+    loss = crit2(net2(x), torch.tensor([0, 1, 0, 1, 1]))
+    loss.backward()
+    assert all(p.grad is not None for p in net.parameters())
+    unswap_modules(net)
+    assert "forward" not in vars(net[0])

@@ -187,7 +187,7 @@ def test_hogwild_gpu_single_worker_equals_sequential_adam():
     torch.manual_seed(3)
     net = MnistCNN(p_drop=0.0)
     dev = torch.device("cuda", 0)
-    cfg = TrainConfig(iters=15, mini_batch=64, device="cuda", seed=11)
+    cfg = TrainConfig(iters=15, mini_batch=64, device="cuda", seed=11, precision="fp32")     # fp32 autograd: exact oracle
     hw = train_partition_hogwild(0, 1, copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, cfg,
                                  dev, acquire_lock=True, window_len=1)
     ref = _fit(net, nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=15, mini_batch=64, engine="eager_plain",

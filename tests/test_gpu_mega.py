@@ -110,3 +110,26 @@ def test_early_stop_random_sampling_and_streaming_paths():
     assert b.history["streaming"] and b.history["step_kernel"]["steps_per_launch"] == 1
     np.testing.assert_allclose(a.history["train_loss"], b.history["train_loss"], rtol=1e-3, atol=1e-4)
     assert c.history["gpu_launches_per_step"] == 2 and c.history["train_loss"][-1] < c.history["train_loss"][0]
+
+
+def test_checkpoint_resume_is_bit_exact_on_the_fused_path(tmp_path):
+    """checkpointDir keeps the K-STEP engine (round 1 fell back to the eager engine): 30 straight steps == 20 steps, a new
+    process-equivalent fit that resumes from the checkpoint, 10 more - bit for bit (deterministic reductions, the step
+    kernel takes iteration / optimizer-step numbers as launch parameters)."""
+    from sparktorch_b200.models import mnist_dnn
+
+    X, Y = _data(n=2048)
+    torch.manual_seed(5)
+    net = mnist_dnn()
+    kw = dict(mini_batch=256, sampling="sweep")
+    straight = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=30, **kw)
+    d = str(tmp_path / "ck")
+    first = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=20, checkpoint_dir=d,
+                 checkpoint_every=10, **kw)
+    assert first.history["step_kernel"] is not None and first.history["iters_run"] == 20
+    resumed = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=30, checkpoint_dir=d,
+                   checkpoint_every=10, resume=True, **kw)
+    assert resumed.history["resumed_from"] == 20 and resumed.history["iters_run"] == 30 and resumed.history["step_kernel"] is not None
+    assert resumed.history["train_loss"] == straight.history["train_loss"]
+    for k in straight.state_dict:
+        assert torch.equal(resumed.state_dict[k], straight.state_dict[k]), k
