@@ -378,6 +378,11 @@ def run_resnet50(args):
 
 
 if __name__ == "__main__":
+    # a run that is killed from outside (timeout, torchrun tearing the job down) says where every thread was
+    import faulthandler
+    import signal
+
+    faulthandler.register(signal.SIGTERM, all_threads=True, chain=True)
     a = parse_args()
     if a.model == "resnet50":
         run_resnet50(a)

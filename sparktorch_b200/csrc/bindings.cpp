@@ -349,7 +349,7 @@ class Updater {
           const Tensor& state, const OptT& loss_hist, int64_t host_mailbox_ptr, const Tensor& segs, int64_t numel,
           int64_t tail, int64_t kind, double lr, double beta1, double beta2, double eps, double weight_decay, double momentum,
           double dampening, bool nesterov, bool maximize, int64_t patience, bool zero_grads, int64_t recv_local_ptr,
-          int64_t recv_stride)
+          int64_t recv_stride, int64_t mc_param_ptr, int64_t mc_wbf16_ptr)
       : state_(state), segs_(segs), m_(m), v_(v), loss_hist_(loss_hist) {
     TORCH_CHECK(world >= 1 && world <= 8, "world size 1..8 (one NVSwitch domain)");
     a_ = st::UpdateArgs{};
@@ -361,6 +361,8 @@ class Updater {
       a_.flags[r] = flag_ptrs.empty() ? nullptr : reinterpret_cast<uint32_t*>(flag_ptrs[r]);
     }
     a_.mc_grad = reinterpret_cast<float*>(mc_grad_ptr);
+    a_.mc_param = reinterpret_cast<float*>(mc_param_ptr);
+    a_.mc_wbf16 = reinterpret_cast<__nv_bfloat16*>(mc_wbf16_ptr);
     a_.m = m ? m->data_ptr<float>() : nullptr;
     a_.v = v ? v->data_ptr<float>() : nullptr;
     TORCH_CHECK(state.numel() * state.element_size() >= int64_t(sizeof(st::StepState)), "state tensor too small");
@@ -574,6 +576,8 @@ class GraphRunner {
   ~GraphRunner() {
     if (exec_) cudaGraphExecDestroy(exec_);
     if (graph_) cudaGraphDestroy(graph_);
+    if (tail_exec_) cudaGraphExecDestroy(tail_exec_);
+    if (tail_graph_) cudaGraphDestroy(tail_graph_);
     for (auto e : copied_) cudaEventDestroy(e);
     for (auto e : consumed_) cudaEventDestroy(e);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -605,6 +609,15 @@ class GraphRunner {
     streaming_ = true;
   }
 
+  // The graph captured next (begin_capture/end_capture) runs `spl` training steps per launch (a K-STEP kernel with n_steps =
+  // spl); the previously captured one-step graph stays as the tail graph for iteration counts that are no multiple of spl.
+  void keep_as_tail_and_expect(int64_t spl) {
+    TORCH_CHECK(exec_ != nullptr && spl >= 1, "capture the one-step graph first");
+    tail_exec_ = exec_; tail_graph_ = graph_;
+    exec_ = nullptr; graph_ = nullptr;
+    spl_ = spl;
+  }
+
   // returns number of iterations launched; stops early when the device latched a stop in the mailbox
   int64_t run(int64_t first_iter, int64_t iters, int64_t mailbox_ptr, int64_t check_every) {
     TORCH_CHECK(exec_ != nullptr, "no captured graph");
@@ -612,23 +625,34 @@ class GraphRunner {
     cudaStream_t s = cur_stream();
     int64_t done = 0;
     const int64_t windows = streaming_ ? (n_rows_ / batch_) : 0;
-    for (int64_t k = 0; k < iters; ++k) {
-      const int64_t i = first_iter + k;
+    int64_t k = 0;
+    while (k < iters) {
+      // steps of this launch: spl_ with the main graph, 1 with the tail graph
+      const bool big = spl_ > 1 && iters - k >= spl_;
+      const int64_t n = big ? spl_ : 1;
+      cudaGraphExec_t ex = (spl_ > 1 && !big) ? tail_exec_ : exec_;
       if (streaming_) {
-        const int slot = int(i % ring_);
-        if (i >= ring_) cudaStreamWaitEvent(copy_stream_, consumed_[slot], 0);
-        const int64_t row0 = (i % windows) * batch_;
-        cudaMemcpyAsync(dx_ + size_t(slot) * batch_ * xrb_, hx_ + size_t(row0) * xrb_, size_t(batch_) * xrb_, cudaMemcpyHostToDevice, copy_stream_);
-        if (hy_ != nullptr)
-          cudaMemcpyAsync(dy_ + size_t(slot) * batch_ * yrb_, hy_ + size_t(row0) * yrb_, size_t(batch_) * yrb_, cudaMemcpyHostToDevice, copy_stream_);
-        cudaEventRecord(copied_[slot], copy_stream_);
-        cudaStreamWaitEvent(s, copied_[slot], 0);
-        h2d_bytes_ += uint64_t(batch_) * uint64_t(xrb_ + (hy_ ? yrb_ : 0));
+        int last_slot = 0;
+        for (int64_t j = 0; j < n; ++j) {
+          const int64_t i = first_iter + k + j;
+          const int slot = int(i % ring_);
+          if (i >= ring_) cudaStreamWaitEvent(copy_stream_, consumed_[slot], 0);
+          const int64_t row0 = (i % windows) * batch_;
+          cudaMemcpyAsync(dx_ + size_t(slot) * batch_ * xrb_, hx_ + size_t(row0) * xrb_, size_t(batch_) * xrb_, cudaMemcpyHostToDevice, copy_stream_);
+          if (hy_ != nullptr)
+            cudaMemcpyAsync(dy_ + size_t(slot) * batch_ * yrb_, hy_ + size_t(row0) * yrb_, size_t(batch_) * yrb_, cudaMemcpyHostToDevice, copy_stream_);
+          h2d_bytes_ += uint64_t(batch_) * uint64_t(xrb_ + (hy_ ? yrb_ : 0));
+          last_slot = slot;
+        }
+        cudaEventRecord(copied_[last_slot], copy_stream_);       // the copy stream is in order: the last batch implies the others
+        cudaStreamWaitEvent(s, copied_[last_slot], 0);
       }
-      TORCH_CHECK(cudaGraphLaunch(exec_, s) == cudaSuccess, "graph launch failed");
-      if (streaming_) cudaEventRecord(consumed_[int(i % ring_)], s);
-      ++done;
-      if (mb != nullptr && check_every > 0 && (k % check_every) == check_every - 1 && mb[0] != 0) break;
+      TORCH_CHECK(cudaGraphLaunch(ex, s) == cudaSuccess, "graph launch failed");
+      if (streaming_)
+        for (int64_t j = 0; j < n; ++j) cudaEventRecord(consumed_[int((first_iter + k + j) % ring_)], s);
+      done += n;
+      k += n;
+      if (mb != nullptr && check_every > 0 && mb[0] != 0) break;
     }
     return done;
   }
@@ -636,8 +660,9 @@ class GraphRunner {
 
  private:
   cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
-  cudaGraph_t graph_ = nullptr;
-  cudaGraphExec_t exec_ = nullptr;
+  cudaGraph_t graph_ = nullptr, tail_graph_ = nullptr;
+  cudaGraphExec_t exec_ = nullptr, tail_exec_ = nullptr;
+  int64_t spl_ = 1;
   int64_t n_nodes_ = 0;
   bool streaming_ = false;
   const char *hx_ = nullptr, *hy_ = nullptr;
@@ -709,7 +734,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<Updater>(m, "Updater")
       .def(py::init<int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,
                     int64_t, const OptT&, const OptT&, const Tensor&, const OptT&, int64_t, const Tensor&, int64_t, int64_t,
-                    int64_t, double, double, double, double, double, double, double, bool, bool, int64_t, bool, int64_t, int64_t>())
+                    int64_t, double, double, double, double, double, double, double, bool, bool, int64_t, bool, int64_t, int64_t,
+                    int64_t, int64_t>())
       .def("step", &Updater::step)
       .def("publish", &Updater::publish)
       .def("set_lr", &Updater::set_lr);
@@ -745,6 +771,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("end_capture", &GraphRunner::end_capture)
       .def("num_nodes", &GraphRunner::num_nodes)
       .def("setup_streaming", &GraphRunner::setup_streaming)
+      .def("keep_as_tail_and_expect", &GraphRunner::keep_as_tail_and_expect)
       .def("run", &GraphRunner::run, py::call_guard<py::gil_scoped_release>())
       .def("h2d_bytes", &GraphRunner::h2d_bytes);
 }

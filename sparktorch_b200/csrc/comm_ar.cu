@@ -248,10 +248,26 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_update_kernel(const Upda
       const int64_t local = e - sg.offset;            // index inside the parameter (may be padding)
       const int64_t count = int64_t(sg.rows) * sg.cols;
       const float pv[4] = {p.x, p.y, p.z, p.w};
+      // NVLS publication: one multimem.st per value reaches every replica (this one included) through the switch - 1/W of the
+      // egress of the per-peer loop below.  Used for the fp32 master copy and the packed row-major bf16 copy; transposed or
+      // unaligned bf16 layouts keep the per-peer path.
+      bool mc_done_f32 = false, mc_done_bf16 = false;
+      if (MODE == 0 && W > 1 && a.mc_param != nullptr) {
+        if (sg.publish_f32) { st_mc_f4(a.mc_param + e, p); mc_done_f32 = true; }
+        if (a.mc_wbf16 != nullptr && sg.w_off >= 0 && sg.wt_off < 0 && (sg.cols & 3) == 0 && (sg.w_ld & 3) == 0 && (sg.w_off & 3) == 0 &&
+            local + 3 < count) {
+          const int row = int(local / sg.cols), col = int(local % sg.cols);
+          const uint32_t lo = pack_bf16x2(pv[0], pv[1]), hi = pack_bf16x2(pv[2], pv[3]);
+          asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(a.mc_wbf16 + sg.w_off + int64_t(row) * sg.w_ld + col),
+                       "f"(__uint_as_float(lo)), "f"(__uint_as_float(hi)) : "memory");
+          mc_done_bf16 = true;
+        }
+      }
       for (int k = 0; k < n_pub; ++k) {
         const int peer = (MODE == 0) ? (me + k) % W : me;
-        if (MODE == 0 && (sg.publish_f32 || peer == me)) reinterpret_cast<float4*>(a.param[peer])[i4] = p;
-        if (sg.w_off >= 0 || sg.wt_off >= 0) {
+        if (mc_done_f32 && (mc_done_bf16 || (sg.w_off < 0 && sg.wt_off < 0)) && peer != me) continue;   // everything already sent
+        if (MODE == 0 && ((sg.publish_f32 && !mc_done_f32) || peer == me)) reinterpret_cast<float4*>(a.param[peer])[i4] = p;
+        if ((sg.w_off >= 0 || sg.wt_off >= 0) && !mc_done_bf16) {
           __nv_bfloat16* wb = a.wbf16[peer];
           const bool packed = sg.w_off >= 0 && sg.wt_off < 0 && (sg.cols & 3) == 0 && (sg.w_ld & 3) == 0 &&
                               (sg.w_off & 3) == 0 && local + 3 < count;

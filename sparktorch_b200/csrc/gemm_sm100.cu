@@ -319,13 +319,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int lbl_off = (win.flags & 4) ? win_off : 0;     // labels / targets of the fused loss
 
 
+  // The two issuing warps run their loops warp-UNIFORMLY (every lane waits on the mbarrier, `elect.sync` picks the lane that
+  // issues): from a `lane == 0` branch ptxas cannot keep the descriptors / addresses in uniform registers and wraps every
+  // UTMALDG / UTCHMMA / UTCBAR in an R2UR waterfall loop (found with the K-STEP kernel, profiles/kstep_v1_timeline_n1.md).
+  const uint32_t smem_base = smem_u32(smem);
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (i / S::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % S::STAGES;
+      const uint32_t ph = (i / S::STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + s * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
         const bool peer_b = !B_MN && peer.world > 0;
@@ -344,32 +348,34 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N < 16 ? 16 : BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % S::STAGES;
-        const uint32_t ph = (i / S::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N < 16 ? 16 : BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % S::STAGES;
+      const uint32_t ph = (i / S::STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+      const uint32_t sb = sa + S::A_BYTES;
+      const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
+      const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
+      // per UMMA_K=16 step, in units of 16 B of the start-address field:
+      //   K-major : 16 bf16 = 32 B inside the swizzled 128 B row -> +2
+      //   MN-major: 16 K-rows of 128 B = 2048 B                  -> +128
+      constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
+      if (elect_one()) {
         if (prof && i == 0) prof[3] = clock64();
-        const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t sb = sa + S::A_BYTES;
-        const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
-        const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
-        // per UMMA_K=16 step, in units of 16 B of the start-address field:
-        //   K-major : 16 bf16 = 32 B inside the swizzled 128 B row -> +2
-        //   MN-major: 16 K-rows of 128 B = 2048 B                  -> +128
-        constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           umma_f16(tmem_base, da + ka * k, db + kb * k, idesc, (i | k) != 0);
         }
         umma_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+        if (i == num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);              // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -553,15 +559,17 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   pdl_wait();
   pdl_launch_dependents();
 
+  const uint32_t smem_base = smem_u32(smem);
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;                                // k-block counter across tiles (smem ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
-        for (int i = 0; i < num_kb; ++i, ++it) {
-          const int s = it % S::STAGES;
-          const uint32_t ph = (it / S::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+    // whole warp runs the loop, one elected lane issues (see the single-tile kernel)
+    uint32_t it = 0;                                // k-block counter across tiles (smem ring position)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      for (int i = 0; i < num_kb; ++i, ++it) {
+        const int s = it % S::STAGES;
+        const uint32_t ph = (it / S::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + s * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
@@ -579,32 +587,34 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-      constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-        const uint32_t as = t & 1;
-        mbar_wait(&tmem_empty_bar[as], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator stage
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+    constexpr uint64_t ka = A_MN ? 128 : 2, kb = B_MN ? 128 : 2;
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const uint32_t as = t & 1;
+      mbar_wait(&tmem_empty_bar[as], ((t >> 1) & 1) ^ 1);      // epilogue drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * BLOCK_N;
+      for (int i = 0; i < num_kb; ++i, ++it) {
+        const int s = it % S::STAGES;
+        const uint32_t ph = (it / S::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * BLOCK_N;
-        for (int i = 0; i < num_kb; ++i, ++it) {
-          const int s = it % S::STAGES;
-          const uint32_t ph = (it / S::STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
-          const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
-          const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
+        const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint64_t da = A_MN ? make_mnmajor_sw128_desc(sa, BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
+        const uint64_t db = B_MN ? make_mnmajor_sw128_desc(sb, BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16(tacc, da + ka * k, db + kb * k, idesc, (i | k) != 0);
           umma_commit(&empty_bar[s]);
+          if (i == num_kb - 1) umma_commit(&tmem_full_bar[as]);
         }
-        umma_commit(&tmem_full_bar[as]);
+        __syncwarp();
       }
     }
   } else {

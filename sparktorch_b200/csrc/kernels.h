@@ -71,6 +71,8 @@ struct UpdateArgs {
   __nv_bfloat16* wbf16[8];    // bf16 weight arena
   uint32_t* flags[8];         // signal pads [2][8][MAX_BLOCKS]
   float* mc_grad;             // multicast (NVLS) alias of the gradient arena or null
+  float* mc_param;            // multicast aliases of the parameter / bf16 arenas: updated values are published with ONE
+  __nv_bfloat16* mc_wbf16;    // multimem.st through the switch instead of one store per peer (null: per-peer stores)
   float* m;                   // optimizer state (owned shard only is touched)
   float* v;
   StepState* state;

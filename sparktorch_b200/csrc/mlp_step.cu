@@ -45,7 +45,10 @@ constexpr int MS_ACC_COLS = 64;                           // TMEM columns per ac
 constexpr int MS_TMEM_COLS = 2 * MS_ACC_COLS;
 constexpr int MS_MISC_BYTES = 2048;                       // barriers, tmem slot, bias tile, column sums, loss, flags
 constexpr int MS_EPI_THREADS = MS_THREADS - 64;          // warps 2.. : two groups of four warps (one per TMEM lane quadrant)
-constexpr int MS_SMEM_TOTAL = MS_STAGES * MS_STAGE_BYTES + MS_MISC_BYTES + int(sizeof(MsPeerTable)) +
+constexpr int MS_CHAIN_BYTES = MS_BLOCK_M * 128;          // dZ_L of a chained head: 128 rows x one 128-byte swizzle row (K <= 64)
+constexpr int MS_CHAIN_OFF = MS_STAGES * MS_STAGE_BYTES;  // 1024-byte aligned (the stages are)
+constexpr int MS_MISC_OFF = MS_CHAIN_OFF + MS_CHAIN_BYTES;
+constexpr int MS_SMEM_TOTAL = MS_MISC_OFF + MS_MISC_BYTES + int(sizeof(MsPeerTable)) +
                               MS_MAX_TASKS * int(sizeof(MsTask)) + 1024;
 static_assert((MS_STAGES & (MS_STAGES - 1)) == 0, "ring index uses a mask");
 
@@ -121,9 +124,10 @@ struct MsShared {
   uint64_t empty_bar[MS_STAGES];
   uint64_t tmem_full_bar[2];
   uint64_t tmem_empty_bar[2];
+  uint64_t chain_bar;       // "dZ_L is in the chain buffer": one arrive per epilogue warp of the first group
   uint32_t tmem_ptr;
   uint32_t stop;            // early-stop decision of the current step (update tasks)
-  uint32_t pad_[2];         // (keeps bias / colsum 16-byte aligned for the vector loads of the lean epilogues)
+  uint32_t pad_[4];         // (keeps bias / colsum 16-byte aligned for the vector loads of the lean epilogues)
   float loss_w[4];          // loss partial of the current tile, one slot per epilogue warp of the first group
   float bias[64];
   float colsum[4][64];      // column sums of the current tile per TMEM lane quadrant (summed in a fixed order: run-to-run bit-exact)
@@ -170,7 +174,7 @@ ST_DEVINL void ms_wait_warp(const MsTask* t, int ti, const MsParams& p, uint32_t
     kind &= 15;
     if (kind == 1 && r == 0) {
       target = (epoch - uint32_t(t->wait[w].mask)) * uint32_t(t->wait[w].need);   // mask = lag in steps
-      ptr = p.counters + t->wait[w].idx;
+      ptr = p.counters + t->wait[w].idx * MS_CNT_STRIDE;
     } else if (kind == 2 && ((t->wait[w].mask >> r) & 1)) {
       target = epoch - uint32_t(t->wait[w].need);      // need = lag: 1 waits for the PREVIOUS step's flag
       ptr = p.flags_local + t->wait[w].idx * 8 + r;
@@ -204,10 +208,10 @@ ST_DEVINL void ms_wait_warp(const MsTask* t, int ti, const MsParams& p, uint32_t
 ST_DEVINL void ms_signal(const MsTask* t, const MsPeerTable* peers, const MsParams& p, uint32_t epoch) {
   if (t->sig_cnt < 0) return;
   if (t->sig_flag < 0) {       // nobody needs the count: release-increment, no round trip
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + t->sig_cnt), "r"(1u) : "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + t->sig_cnt * MS_CNT_STRIDE), "r"(1u) : "memory");
     return;
   }
-  const uint32_t old = atom_add_acqrel_gpu(p.counters + t->sig_cnt, 1u);
+  const uint32_t old = atom_add_acqrel_gpu(p.counters + t->sig_cnt * MS_CNT_STRIDE, 1u);
   if (old + 1u == epoch * uint32_t(t->sig_total)) {
     if (p.world > 1) fence_acqrel_sys();
     for (int r = 0; r < p.world; ++r)
@@ -220,7 +224,7 @@ ST_DEVINL void ms_fetch_decision(MsShared* sh, const MsParams& p, int ti, uint32
   if (lane == 0) {
     uint32_t stop = 0;
     if (p.patience > 0) {
-      const uint32_t* d = p.counters + p.decide_cnt;
+      const uint32_t* d = p.counters + p.decide_cnt * MS_CNT_STRIDE;
       uint32_t val, spins = 0;
       unsigned long long t0 = 0;
       while (int32_t(((val = ld_relaxed_gpu_u32(d)) >> 1) - epoch) < 0) {
@@ -344,10 +348,12 @@ __device__ __noinline__ void ms_epilogue_rolled(const MsTask* t, MsShared* sh, c
   const int row = t->m0 + q * 32 + lane;
   const bool row_ok = row < t->M;
   // the two epilogue warp groups split the tile's columns in whole 8-column groups
-  const int ncols_all = min(t->block_n, t->N - t->n0);   // valid columns of this tile (> 0)
-  const int c_split = ((ncols_all + 15) >> 4) << 3;
-  const int c_begin = half ? c_split : 0;
-  const int ncols = (half ? ncols_all : min(c_split, ncols_all)) - c_begin;     // this group's columns (may be <= 0)
+  const int w0 = t->ep_c0, wc = t->ep_cols ? t->ep_cols : t->block_n;     // epilogue window of this task inside the tile
+  const int ncols_all = min(wc, t->N - t->n0 - w0);      // valid columns of the window
+  const int c_split = ((max(ncols_all, 0) + 15) >> 4) << 3;
+  const int c_rel = half ? c_split : 0;
+  const int c_begin = w0 + c_rel;
+  const int ncols = (half ? ncols_all : min(c_split, ncols_all)) - c_rel;       // this group's columns (may be <= 0)
   const int n0 = t->n0 + c_begin;
   tacc += uint32_t(c_begin);
   const bool have_mask = (flags & MS_MASK) != 0;
@@ -676,12 +682,14 @@ ST_DEVINL bool ms_epilogue_lean(const MsTask* t, MsShared* sh, const MsParams& p
                                 uint64_t* tmem_empty, uint64_t* tmem_full, uint32_t full_parity, int64_t step1, long long* stamp_slot,
                                 int half) {
   const int flags = t->flags;
-  const int ncols_all = min(t->block_n, t->N - t->n0);
-  if ((ncols_all & 7) != 0) return false;
+  const int w0 = t->ep_c0, wc = t->ep_cols ? t->ep_cols : t->block_n;     // epilogue window of this task inside the tile
+  const int ncols_all = min(wc, t->N - t->n0 - w0);
+  if (ncols_all <= 0 || (ncols_all & 7) != 0 || (w0 & 7) != 0) return false;
   if ((flags & MS_OUT_F32) && (((t->ld_f32 & 3) != 0) || (flags & MS_OUT_BF16))) return false;
   const int c_split = ((ncols_all + 15) >> 4) << 3;
-  const int c_begin = half ? c_split : 0;
-  const int ncols = (half ? ncols_all : min(c_split, ncols_all)) - c_begin;
+  const int c_rel = half ? c_split : 0;
+  const int c_begin = w0 + c_rel;
+  const int ncols = (half ? ncols_all : min(c_split, ncols_all)) - c_rel;
   const int row = t->m0 + q * 32 + lane;
   const bool row_ok = row < t->M;
   ms_mbar_wait(tmem_full, full_parity, p, 13);
@@ -721,7 +729,7 @@ ST_DEVINL bool ms_epilogue_lean(const MsTask* t, MsShared* sh, const MsParams& p
 template <int NC>
 ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p, int par, uint32_t tacc, int q, int lane,
                                 int lbl_off, uint64_t* tmem_empty, uint64_t* tmem_full, uint32_t full_parity,
-                                long long* stamp_slot, int half) {
+                                long long* stamp_slot, int half, uint8_t* chain) {
   if (half) {                                    // the row-wise loss is done by the first warp group alone
     ms_mbar_wait(tmem_full, full_parity, p, 13);
     tc_fence_before();
@@ -782,16 +790,24 @@ ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p
   for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
   if (lane == 0) sh->loss_w[q] = li * t->loss_scale;
   // dZ_L (bf16): whole 8-column groups up to the pitch (a multiple of 8); columns >= N inside them are written as zeros
-  if (row_ok) {
+  {
+    const bool to_global = row_ok && !(flags & MS_QUIET);
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(t->out_bf16[par]) + size_t(row) * t->ld_out;
+    const int rl = q * 32 + lane;              // row inside the tile = row of the chain buffer
 #pragma unroll
     for (int v = 0; v < NC / 8; ++v) {
-      if (8 * v < N && 8 * v + 8 <= t->ld_out) {
-        uint4 w;
-        w.x = pack_bf16x2(acc[8 * v + 0], acc[8 * v + 1]); w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
-        w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]); w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
-        reinterpret_cast<uint4*>(op)[v] = w;
-      }
+      uint4 w;
+      w.x = pack_bf16x2(acc[8 * v + 0], acc[8 * v + 1]); w.y = pack_bf16x2(acc[8 * v + 2], acc[8 * v + 3]);
+      w.z = pack_bf16x2(acc[8 * v + 4], acc[8 * v + 5]); w.w = pack_bf16x2(acc[8 * v + 6], acc[8 * v + 7]);
+      if (to_global && 8 * v < N && 8 * v + 8 <= t->ld_out) reinterpret_cast<uint4*>(op)[v] = w;
+      // chain buffer: K-major operand with the 128-byte swizzle the MMA descriptor expects (16-byte chunk c of row r sits
+      // at chunk c ^ (r & 7)); rows past M and columns past N carry zeros (acc is zero there)
+      if (chain != nullptr) *reinterpret_cast<uint4*>(chain + rl * 128 + ((v ^ (rl & 7)) << 4)) = w;
+    }
+    if (chain != nullptr) {
+      fence_proxy_async_all();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->chain_bar);
     }
   }
   if (flags & MS_COLSUM) {
@@ -888,7 +904,7 @@ ST_DEVINL void ms_decide(const MsTask* t, const MsParams& p, const MsPeerTable* 
     }
   }
   st->pad[0] = epoch;                    // steps run since the counters were zeroed (advances even when stopped)
-  if (p.patience > 0) st_release_gpu_u32(p.counters + p.decide_cnt, epoch * 2u + stop_bit);
+  if (p.patience > 0) st_release_gpu_u32(p.counters + p.decide_cnt * MS_CNT_STRIDE, epoch * 2u + stop_bit);
   ms_signal(t, peers, p, epoch);
 }
 
@@ -906,9 +922,10 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
   }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  MsShared* sh = reinterpret_cast<MsShared*>(smem + MS_STAGES * MS_STAGE_BYTES);
-  MsPeerTable* peers = reinterpret_cast<MsPeerTable*>(smem + MS_STAGES * MS_STAGE_BYTES + MS_MISC_BYTES);
-  MsTask* s_tasks = reinterpret_cast<MsTask*>(smem + MS_STAGES * MS_STAGE_BYTES + MS_MISC_BYTES + sizeof(MsPeerTable));
+  uint8_t* chain = smem + MS_CHAIN_OFF;
+  MsShared* sh = reinterpret_cast<MsShared*>(smem + MS_MISC_OFF);
+  MsPeerTable* peers = reinterpret_cast<MsPeerTable*>(smem + MS_MISC_OFF + MS_MISC_BYTES);
+  MsTask* s_tasks = reinterpret_cast<MsTask*>(smem + MS_MISC_OFF + MS_MISC_BYTES + sizeof(MsPeerTable));
 
   const int warp = ubc(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -924,6 +941,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
       mbar_init(&sh->tmem_full_bar[a], 1);
       mbar_init(&sh->tmem_empty_bar[a], MS_EPI_THREADS / 32);   // one arrive per epilogue warp
     }
+    mbar_init(&sh->chain_bar, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -943,6 +961,9 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
     }
     if (threadIdx.x < 4) sh->loss_w[threadIdx.x] = 0.f;
     if (threadIdx.x == 0) sh->stop = 0;
+    // chain buffer: only the 16-byte chunks that hold dZ_L are ever written again, the rest stays zero (K padding of the MMA)
+    for (int i = threadIdx.x; i < MS_CHAIN_BYTES / 16; i += MS_THREADS) reinterpret_cast<uint4*>(chain)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -970,7 +991,8 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
         const int a_row_off = (flags & MS_A_WIN) ? win_off : 0;
         const int b_k_off = (flags & MS_B_WIN) ? win_off : 0;
         const int m0 = ubc(t->m0), n0 = ubc(t->n0), nkb = ubc(t->num_kb);
-        const uint32_t tx = uint32_t(MS_A_BYTES) + (b_mn ? uint32_t(MS_B_BYTES) : uint32_t(ubc(t->block_n)) * 128u);
+        const bool chain_tail = (flags & MS_CHAIN_TAIL) != 0;     // A comes from the chain buffer: only B travels
+        const uint32_t tx = (chain_tail ? 0u : uint32_t(MS_A_BYTES)) + (b_mn ? uint32_t(MS_B_BYTES) : uint32_t(ubc(t->block_n)) * 128u);
         const int pre = nkb < MS_STAGES ? nkb : MS_STAGES;      // stages armed before the late dependencies are met
         if (elect_one()) {
           if (stamp) prof[ti * 8 + 0] = (long long)globaltimer_ns();
@@ -1012,7 +1034,8 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
               if (b_mn) tma_load_2d(sb, mb, &sh->full_bar[st_], n0, k0 + b_k_off);
               else tma_load_2d(sb, mb, &sh->full_bar[st_], k0, n0);
             }
-            if (a_mn) {
+            if (chain_tail) {
+            } else if (a_mn) {
               tma_load_2d(sa, ma, &sh->full_bar[st_], m0, k0);
               tma_load_2d(sa + MS_BLOCK_K * 128, ma, &sh->full_bar[st_], m0 + 64, k0);
             } else {
@@ -1026,7 +1049,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp waits, one elected lane issues) =====================
-    uint32_t kbc = 0, gc = 0;
+    uint32_t kbc = 0, gc = 0, cc = 0;
     for (int s = 0; s < p.n_steps; ++s) {
       const bool stamp = prof != nullptr && s == p.n_steps - 1;
       for (int ti = 0; ti < n_tasks; ++ti) {
@@ -1035,6 +1058,11 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
         const int flags = ubc(t->flags);
         const uint32_t as = gc & 1;
         ms_mbar_wait(&sh->tmem_empty_bar[as], ((gc >> 1) & 1) ^ 1, p, 11);
+        const bool chain_tail = (flags & MS_CHAIN_TAIL) != 0;
+        if (chain_tail) {                       // the head's epilogue warps have put dZ_L into the chain buffer
+          ms_mbar_wait(&sh->chain_bar, cc & 1, p, 14);
+          ++cc;
+        }
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * MS_ACC_COLS;
         const bool a_mn = (flags & MS_A_MN) != 0, b_mn = (flags & MS_B_MN) != 0;
@@ -1049,7 +1077,8 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           tc_fence_after();
           const uint32_t sa = smem_base + st_ * MS_STAGE_BYTES;
           const uint32_t sb = sa + MS_A_BYTES;
-          const uint64_t da = a_mn ? make_mnmajor_sw128_desc(sa, MS_BLOCK_K * 128) : make_kmajor_sw128_desc(sa);
+          const uint64_t da = chain_tail ? make_kmajor_sw128_desc(smem_base + MS_CHAIN_OFF)
+                                         : (a_mn ? make_mnmajor_sw128_desc(sa, MS_BLOCK_K * 128) : make_kmajor_sw128_desc(sa));
           const uint64_t db = b_mn ? make_mnmajor_sw128_desc(sb, MS_BLOCK_K * 128) : make_kmajor_sw128_desc(sb);
           if (elect_one()) {
             if (stamp) {
@@ -1105,17 +1134,19 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           const uint32_t tacc = tmem_base + (uint32_t(q * 32) << 16) + as * MS_ACC_COLS;
           long long* slot5 = (stamp && et == 0) ? &prof[ti * 8 + 5] : nullptr;
           if (flags & (MS_LOSS_CE | MS_LOSS_MSE)) {
+            uint8_t* cb = (flags & MS_CHAIN_HEAD) ? chain : nullptr;
             if (N <= 16) ms_epilogue_loss<16>(t, sh, p, par, tacc, q, lane, (flags & MS_LBL_WIN) ? win_off : 0, &sh->tmem_empty_bar[as],
-                                              &sh->tmem_full_bar[as], (gc >> 1) & 1, slot5, half);
+                                              &sh->tmem_full_bar[as], (gc >> 1) & 1, slot5, half, cb);
             else ms_epilogue_loss<32>(t, sh, p, par, tacc, q, lane, (flags & MS_LBL_WIN) ? win_off : 0, &sh->tmem_empty_bar[as],
-                                      &sh->tmem_full_bar[as], (gc >> 1) & 1, slot5, half);
+                                      &sh->tmem_full_bar[as], (gc >> 1) & 1, slot5, half, cb);
           } else if (!ms_epilogue_lean(t, sh, p, par, tacc, q, lane, &sh->tmem_empty_bar[as], &sh->tmem_full_bar[as], (gc >> 1) & 1, step1,
                                        slot5, half)) {
             ms_epilogue_rolled(t, sh, p, par, tacc, q, lane, &sh->tmem_empty_bar[as], &sh->tmem_full_bar[as], (gc >> 1) & 1, step1, slot5, half);
           }
-          if (flags & (MS_COLSUM | MS_LOSS_CE | MS_LOSS_MSE)) {
+          if ((flags & (MS_COLSUM | MS_LOSS_CE | MS_LOSS_MSE)) && !(flags & MS_QUIET)) {
             asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");
-            if ((flags & MS_COLSUM) && et < bn) {
+            const int wlo = t->ep_c0, whi = t->ep_cols ? t->ep_c0 + t->ep_cols : bn;
+            if ((flags & MS_COLSUM) && et >= wlo && et < whi) {
               if (n0 + et < N)
                 reinterpret_cast<float*>(t->colsum)[n0 + et] = ((sh->colsum[0][et] + sh->colsum[1][et]) + sh->colsum[2][et]) + sh->colsum[3][et];
             }

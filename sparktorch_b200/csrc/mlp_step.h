@@ -31,7 +31,14 @@ enum MsFlags : int32_t {
   MS_LOSS_MSE = 1 << 11,
   MS_LBL_WIN = 1 << 12,    // labels / targets are the resident partition's (offset by the window)
   MS_FUSED_OPT = 1 << 13,  // one GPU: the weight-gradient tile applies the optimizer to its parameters in the epilogue
+  // Chained head: the CTA that runs a tile of the last layer's dgrad (dZ_{L-1} = dZ_L W_L) recomputes the head of its 128
+  // rows itself (logits, loss, dZ_L) and feeds dZ_L to the second MMA through shared memory - the step loses a whole
+  // signal -> wait -> load -> store phase.  A pair of consecutive tasks on one CTA:
+  MS_CHAIN_HEAD = 1 << 14, // head tile whose epilogue also writes dZ_L (bf16, 128B-swizzled K-major) into the chain buffer
+  MS_QUIET = 1 << 15,      // redundant copy of a head tile: nothing is stored to global memory, nothing is signalled
+  MS_CHAIN_TAIL = 1 << 16, // A operand = the chain buffer (no TMA load of A)
 };
+constexpr int MS_CNT_STRIDE = 32;        // one dependency counter per 128-byte line (words): polls of different counters never share a line
 
 struct MsWait {            // kind 0: none; 1: local counter (>= epoch * need); 2: cross-GPU flag `idx` from every rank in `mask` (>= epoch)
   int32_t kind, idx, need, mask;
@@ -58,7 +65,8 @@ struct MsTask {
   int64_t part_off, part_stride;         // UPDATE: partial p >= 1 of element e lives at part_off + (p - 1) * part_stride + e
   MsWait wait[3];
   int32_t sig_cnt, sig_total, sig_flag, sig_mask;   // bump counter; when it reaches epoch * sig_total raise flag on ranks in mask
-  int32_t pad[2];
+  int32_t ep_c0, ep_cols;                // epilogue window inside the tile (ep_cols = 0: the whole tile).  Two CTAs may run the same
+                                         // MMA tile and drain half of its columns each: the epilogue, not the MMA, is the cost.
 };
 static_assert(sizeof(MsTask) == 256, "MsTask layout is mirrored in Python");
 

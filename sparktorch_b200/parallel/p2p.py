@@ -135,7 +135,16 @@ class FusedUpdate:
             self.block.peer_ptrs("wbf16") if self.wbf16 is not None else [], flags, mc, self.m, self.v, self.state,
             self.loss_hist, self.mailbox.data_ptr(), self._segs, self.numel, TAIL, s.kind_id, s.lr, s.beta1, s.beta2,
             s.eps, s.weight_decay, s.momentum, s.dampening, s.nesterov, s.maximize, self.patience, zero_grads,
-            self.block.peer_ptrs("recv")[self.rank] if self.exchange == "push" else 0, self.recv_stride)
+            self.block.peer_ptrs("recv")[self.rank] if self.exchange == "push" else 0, self.recv_stride,
+            # NVLS publication of the updated values (SPARKTORCH_NVLS_PUBLISH=0: per-peer stores as in round 1)
+            self.block.multicast_ptr("param") if (self.use_multicast and self._mc_publish()) else 0,
+            self.block.multicast_ptr("wbf16") if (self.use_multicast and self._mc_publish() and self.wbf16 is not None) else 0)
+
+    @staticmethod
+    def _mc_publish() -> bool:
+        import os
+
+        return os.environ.get("SPARKTORCH_NVLS_PUBLISH", "1") == "1"
 
     def push_kw(self, mask: int) -> dict:
         """Arguments that make a GEMM mirror its gradient-arena writes into my slot on every peer."""

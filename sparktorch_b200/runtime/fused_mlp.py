@@ -454,7 +454,11 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
 
         dist.broadcast(plan.arena.flat_p, src=0)      # rank 0's weights win (quirk Q7)
     stream = torch.cuda.Stream(device=device)
-    ring = 3
+    # staging slots for streamed batches: with the K-STEP kernel a launch runs `stream_spl` steps, the copy stream stays a few
+    # launches ahead (3 launches worth of slots)
+    stream_spl = max(1, int(os.environ.get("SPARKTORCH_STREAM_STEPS", "4")))
+    mlp_candidate = lower_mlp(model) is not None and os.environ.get("SPARKTORCH_MEGA", "1") == "1"
+    ring = 3 * stream_spl if (mlp_candidate and cfg.streaming and cfg.early_stop_patience <= 0 and not cfg.verbose) else 3
     runner = C.GraphRunner()
     seed = int(rng.integers(0, 2**62)) if cfg.seed is None else int(cfg.seed) * 1000003 + rank
     with torch.cuda.stream(stream):
@@ -554,6 +558,12 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
                                    plan.train["acts"][0], None, plan.train["tgt"], plan.fu.state)
                 mega_step.run(-1, 0, 0, 1)
                 runner.end_capture()
+                if streaming and ring == 3 * stream_spl and stream_spl > 1:
+                    # main graph: stream_spl steps per launch (the one-step graph above serves ragged tails)
+                    runner.keep_as_tail_and_expect(stream_spl)
+                    runner.begin_capture()
+                    mega_step.run(-1, 0, 0, stream_spl)
+                    runner.end_capture()
             launches = 1 + (1 if gathered else 0)
         if mega is None:
             # warm-up launch outside capture (module load, smem attributes), then rewind the step state
@@ -724,7 +734,8 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
     losses = plan.fu.loss_hist[:n_done].cpu().tolist()
     history = {
         "engine": "fused_resnet" if is_resnet else ("fused_cnn" if is_cnn else "fused_mlp"),
-        "step_kernel": (dict(mega.describe(), steps_per_launch=1 if mega_graph else steps_per_launch) if mega is not None else None),
+        "step_kernel": (dict(mega.describe(), steps_per_launch=((stream_spl if (streaming and ring == 3 * stream_spl) else 1)
+                                                                if mega_graph else steps_per_launch)) if mega is not None else None),
         "comm": ("P2PPush" if getattr(plan.fu, "exchange", "") == "push" else "P2PFused" + ("+NVLS" if plan.fu.use_multicast else "")),
         "precision": "bf16",
         "world_size": world, "train_loss": losses, "stopped_at": (n_done - 1) if stopped else None, "iters_run": n_done,

@@ -35,6 +35,8 @@ MS_MAX_FLAGS = 64
 MS_GEMM, MS_UPDATE, MS_DECIDE = 1, 2, 3
 F_A_MN, F_B_MN, F_RELU, F_A_WIN, F_B_WIN, F_BIAS, F_MASK = 1, 2, 4, 8, 16, 32, 64
 F_OUT_BF16, F_OUT_F32, F_COLSUM, F_LOSS_CE, F_LOSS_MSE, F_LBL_WIN, F_FUSED_OPT = 128, 256, 512, 1024, 2048, 4096, 8192
+F_CHAIN_HEAD, F_QUIET, F_CHAIN_TAIL = 1 << 14, 1 << 15, 1 << 16
+CNT_STRIDE = 32            # words between dependency counters on the device (MS_CNT_STRIDE in csrc/mlp_step.h)
 
 # mirrors struct MsTask (csrc/mlp_step.h), 256 bytes
 MS_TASK = np.dtype([
@@ -44,7 +46,7 @@ MS_TASK = np.dtype([
     ("bias", "<i8"), ("mask", "<i8", 2), ("out_bf16", "<i8", 2), ("out_f32", "<i8"), ("colsum", "<i8"),
     ("labels", "<i8"), ("loss_slot", "<i8", 2), ("loss_scale", "<f4"), ("seg", "<i4"), ("e0", "<i8"),
     ("len", "<i4"), ("n_part", "<i4"), ("part_off", "<i8"), ("part_stride", "<i8"),
-    ("wait", "<i4", (3, 4)), ("sig", "<i4", 4), ("pad", "<i4", 2)])
+    ("wait", "<i4", (3, 4)), ("sig", "<i4", 4), ("ep_c0", "<i4"), ("ep_cols", "<i4")])
 assert MS_TASK.itemsize == 256
 
 
@@ -192,7 +194,15 @@ class MegaPlan:
         #  the separate, fully coalesced update chunks are faster for the MNIST-sized layers - profiles/kstep_timeline_*.md)
         fused_opt = single and os.environ.get("SPARKTORCH_MEGA_FUSED_OPT", "0") == "1"
         self.fused_opt = fused_opt
-        wg_tiles = {l: _cdiv(d[l], 128) * _cdiv(d[l - 1], 64) for l in range(1, L + 1)}
+        split = int(os.environ.get("SPARKTORCH_MEGA_EPI_SPLIT", "2"))       # CTAs per 64-wide backward tile (1, 2 or 4)
+        if split not in (1, 2, 4):
+            split = 2
+        # chained head: the CTAs of the last layer's dgrad tiles recompute the head (logits, loss, dZ_L) of their rows and feed
+        # dZ_L to the dgrad MMA through shared memory; the separate head phase (and its signal/wait hop) disappears
+        chain = (os.environ.get("SPARKTORCH_MEGA_CHAIN", "1") == "1" and L >= 2 and d[L] <= 32 and not fused_opt)
+        self.chain = chain
+        wg_tiles = {l: _cdiv(d[l], 128) * sum(len([c for c in range(0, 64, 64 // split) if d[l - 1] - nt * 64 - c > 0])
+                                              for nt in range(_cdiv(d[l - 1], 64))) for l in range(1, L + 1)}
 
         def w_pub(sidx: int, early=True):          # "segment sidx as of the previous step is published everywhere"
             if fused_opt and sidx in seg_of_w:
@@ -208,7 +218,7 @@ class MegaPlan:
             t = dict(type=0, flags=0, tmap_a=[0, 0], tmap_b=[0, 0], m0=0, n0=0, M=0, N=0, num_kb=0, block_n=0, ld_mask=0,
                      ld_out=0, ld_f32=0, ld_target=0, bias=0, mask=[0, 0], out_bf16=[0, 0], out_f32=0, colsum=0, labels=0,
                      loss_slot=[0, 0], loss_scale=0.0, seg=0, e0=0, len=0, n_part=1, part_off=0, part_stride=0,
-                     wait=[], sig=[-1, 0, -1, 0], cost=1.0, group="")
+                     wait=[], sig=[-1, 0, -1, 0], ep_c0=0, ep_cols=0, cost=1.0, group="", after_prev=False)
             t.update(kw)
             tasks.append(t)
             return t
@@ -230,6 +240,7 @@ class MegaPlan:
             return _addr(fu.grad, xoff + (mt - 1) * nb + boff[l])
 
         n_f_tiles = [0] * (L + 1)
+        head_of: Dict[int, dict] = {}
         # ---------------------------------------------------------------- forward
         for l in range(1, L + 1):
             bn = bn_fwd(l)
@@ -242,6 +253,9 @@ class MegaPlan:
                 for nt in range(ntl):
                     fl = (F_BIAS if has_bias[l - 1] else 0) | (F_RELU if relu[l - 1] else 0)
                     src_rows = self.x_src.shape[0] if l == 1 else B
+                    if l == L and chain:
+                        assert ntl == 1
+                        tasks_before = len(tasks)
                     t = new_task(type=MS_GEMM, m0=mt * 128, n0=nt * bn, M=B, N=d[l], num_kb=nkb, block_n=bn,
                                  tmap_a=[self._tmap(src_of(l - 1, p), src_rows, K, 128) for p in range(2)],
                                  tmap_b=[self._tmap(Wb, d[l], K, bn)] * 2,
@@ -274,9 +288,16 @@ class MegaPlan:
                         # the head's tiles complete dZ_L, db_L and the loss of this rank: flag gr(b_L) doubles as "loss ready"
                         t["sig"] = [c_dz(L), n_f_tiles[L], -1 if single else f_dz(L), all_mask]
                     t["flags"] = fl
+                    if l == L and chain:        # not a task of its own: the template of the head copies of m-tile mt
+                        del tasks[tasks_before:]
+                        head_of[mt] = t
         self.loss_flag = f_dz(L)
         # ---------------------------------------------------------------- decision
-        new_task(type=MS_DECIDE, wait=[w_cnt(c_dz(L), n_f_tiles[L]) if single else w_flag(self.loss_flag, 0, all_mask)], cost=0.5, group="D")
+        def decide_task():
+            new_task(type=MS_DECIDE, wait=[w_cnt(c_dz(L), n_f_tiles[L]) if single else w_flag(self.loss_flag, 0, all_mask)], cost=0.5, group="D")
+
+        if not chain:           # (chained head: created behind the head copies it waits for - list order is a topological order)
+            decide_task()
         # ---------------------------------------------------------------- backward, last layer first
         n_dz_tiles = [0] * (L + 1)
         n_dz_tiles[L] = n_f_tiles[L]
@@ -293,24 +314,43 @@ class MegaPlan:
         def w_dz(l):       # "dZ_l (and db_l) of this step complete on every replica"
             return w_cnt(c_dz(l), n_dz_tiles[l]) if single else w_flag(f_dz(l), 0, all_mask)
 
+        # the 64-wide backward tile is run by `split` CTAs that drain one window of its columns each (epilogue time ~ columns per thread)
+        wins = lambda nt_, N_: [(c, min(64 // split, N_ - nt_ * 64 - c)) for c in range(0, 64, 64 // split) if N_ - nt_ * 64 - c > 0]   # noqa: E731
         for l in range(L, 0, -1):
-            if has_bias[l - 1]:     # db_l is complete once dZ_l is (column sums of its producers)
-                sb = seg_of_b[l - 1]
-                update_tasks(sb, [w_dz(l)], n_mt, xoff + boff[l] - b_off_arena[l - 1])
+            chained = chain and l == L
+            if l > 1:
+                n_dz_tiles[l - 1] = n_mt * sum(len(wins(nt, d[l - 1])) for nt in range(_cdiv(d[l - 1], 64)))
+            def bias_update():      # db_l is complete once dZ_l is (column sums of its producers)
+                # chained head: the quiet copies of the head read b_L until the last dgrad tile of the layer is done
+                update_tasks(seg_of_b[l - 1], [w_dz(l)] + ([w_dz(l - 1)] if chained else []), n_mt, xoff + boff[l] - b_off_arena[l - 1])
+
+            if has_bias[l - 1] and not chained:
+                bias_update()
             if l > 1:
                 # dgrad: dZ_{l-1}[B, d_{l-1}] = dZ_l[B, d_l] W_l[d_l, d_{l-1}]  (B operand MN-major, 64-wide tiles)
                 K = d[l]
                 nkb = _cdiv(K, 64)
                 ntl = _cdiv(d[l - 1], 64)
-                n_dz_tiles[l - 1] = n_mt * ntl
                 for mt in range(n_mt):
-                    for nt in range(ntl):
+                    for j, (nt, (wc0, wcn)) in enumerate([(nt_, w_) for nt_ in range(ntl) for w_ in wins(nt_, d[l - 1])]):
                         fl = F_B_MN | F_OUT_BF16
+                        if chained:
+                            # the head copy that feeds this tile; the first one of the m-tile is the one that stores dZ_L / db_L /
+                            # the loss partial and signals them, the others keep everything on chip
+                            h = dict(head_of[mt])
+                            h["flags"] |= F_CHAIN_HEAD | (F_QUIET if j else 0)
+                            if j:
+                                h["sig"] = [-1, 0, -1, 0]
+                            h["group"] = f"H{l}"
+                            tasks.append(h)
+                            fl |= F_CHAIN_TAIL
                         t = new_task(type=MS_GEMM, m0=mt * 128, n0=nt * 64, M=B, N=d[l - 1], num_kb=nkb, block_n=64,
                                      tmap_a=[self._tmap(self.dz[l][p], B, K, 128) for p in range(2)],
                                      tmap_b=[self._tmap(plan.Wb[l - 1], K, d[l - 1], 64)] * 2,
                                      out_bf16=[_addr(self.dz[l - 1][p]) for p in range(2)], ld_out=self.dz[l - 1][0].stride(0),
-                                     wait=[w_cnt(c_dz(l), n_dz_tiles[l]), w_pub(seg_of_w[l - 1])], cost=1.2 + 0.15 * nkb, group=f"B{l}")
+                                     ep_c0=wc0, ep_cols=wcn if split > 1 else 0,
+                                     wait=([] if chained else [w_cnt(c_dz(l), n_dz_tiles[l])]) + [w_pub(seg_of_w[l - 1])],
+                                     cost=(0.9 if chained else 1.2) + 0.15 * nkb, group=f"B{l}", after_prev=chained)
                         if relu[l - 2]:
                             fl |= F_MASK
                             t["mask"] = [_addr(self.acts[l - 1][p]) for p in range(2)]
@@ -320,27 +360,34 @@ class MegaPlan:
                             t["colsum"] = colsum_ptr(l - 1, mt)
                         t["sig"] = [c_dz(l - 1), n_dz_tiles[l - 1], -1 if single else f_dz(l - 1), all_mask]
                         t["flags"] = fl
+            if chained:
+                decide_task()
+            if has_bias[l - 1] and chained:       # (after the tiles it waits for: every CTA's list stays a topological order)
+                bias_update()
             # wgrad: dW_l[d_l, d_{l-1}] = dZ_l^T A_{l-1}   (both operands MN-major, reduction over the batch)
             nkb = _cdiv(B, 64)
             mtl, ntl = _cdiv(d[l], 128), _cdiv(d[l - 1], 64)
             sw = seg_of_w[l - 1]
+            gwins = lambda nt_: [(c, min(64 // split, d[l - 1] - nt_ * 64 - c)) for c in range(0, 64, 64 // split) if d[l - 1] - nt_ * 64 - c > 0]   # noqa: E731
+            n_g = mtl * sum(len(gwins(nt)) for nt in range(ntl))
+            wg_tiles[l] = n_g
             for mt in range(mtl):
-                for nt in range(ntl):
+                for nt, (wc0, wcn) in [(nt_, w_) for nt_ in range(ntl) for w_ in gwins(nt_)]:
                     src_rows = self.x_src.shape[0] if l == 1 else B
                     new_task(type=MS_GEMM, flags=F_A_MN | F_B_MN | F_OUT_F32 | (F_B_WIN if (l == 1 and windowed) else 0) | (F_FUSED_OPT if fused_opt else 0),
                              seg=sw, m0=mt * 128, n0=nt * 64, M=d[l], N=d[l - 1], num_kb=nkb, block_n=64,
                              tmap_a=[self._tmap(self.dz[l][p], B, d[l], 64) for p in range(2)],
                              tmap_b=[self._tmap(src_of(l - 1, p), src_rows, d[l - 1], 64) for p in range(2)],
-                             out_f32=_addr(fu.grad, w_off_arena[l - 1]), ld_f32=d[l - 1],
+                             out_f32=_addr(fu.grad, w_off_arena[l - 1]), ld_f32=d[l - 1], ep_c0=wc0, ep_cols=wcn if split > 1 else 0,
                              wait=[w_cnt(c_dz(l), n_dz_tiles[l])] + ([w_cnt(c_act(l - 1), n_f_tiles[l - 1], early=True)] if l > 1 else [])
                              # fused optimizer: this tile overwrites W_l, which this step's dgrad B_l still reads until dZ_{l-1} is complete
-                             + ([w_cnt(c_dz(l - 1), _cdiv(B, 128) * _cdiv(d[l - 1], 64))] if (fused_opt and l > 1) else []),
-                             sig=[c_wg(l), mtl * ntl, -1 if single else f_gw(l), all_mask],
+                             + ([w_cnt(c_dz(l - 1), n_dz_tiles[l - 1])] if (fused_opt and l > 1) else []),
+                             sig=[c_wg(l), n_g, -1 if single else f_gw(l), all_mask],
                              cost=1.5 + 0.15 * nkb, group=f"G{l}")
             # W_l may only be overwritten (on EVERY replica: the owner publishes everywhere) once every replica's dgrad of
             # this step has read it: dZ_{l-1} complete  <=>  the B_l tiles are done
             if not fused_opt:
-                w_gw = w_cnt(c_wg(l), mtl * ntl) if single else w_flag(f_gw(l), 0, all_mask)
+                w_gw = w_cnt(c_wg(l), n_g) if single else w_flag(f_gw(l), 0, all_mask)
                 update_tasks(sw, [w_gw] + ([w_dz(l - 1)] if l > 1 else []), 1, 0)
         self.task_dicts = tasks
         if not self._place():
@@ -362,6 +409,7 @@ class MegaPlan:
         cnt_done: Dict[int, float] = {}
         flag_done: Dict[int, float] = {}
         lists: List[List[int]] = [[] for _ in range(G)]
+        prev_cta = 0
         for ti, t in enumerate(self.task_dicts):
             ready = 0.0
             for k, idx, need, m in t["wait"]:
@@ -369,7 +417,9 @@ class MegaPlan:
                     ready = max(ready, cnt_done.get(idx, 0.0))
                 elif (k & 15) == 2 and need == 0:
                     ready = max(ready, flag_done.get(idx, 0.0) + (1.5 if self.world > 1 else 0.0))
-            if t["type"] == MS_DECIDE:
+            if t.get("after_prev"):
+                best = prev_cta                 # second half of a chained pair: same CTA, right behind the head copy
+            elif t["type"] == MS_DECIDE:
                 # on the CTA of the first forward tile: everything of step s+1 then follows the decision of step s in
                 # program order, which is what keeps the loss partial slots (double buffered) safe to reuse
                 best = next(c for c in range(G) if lists[c] and lists[c][0] == 0)
@@ -381,6 +431,7 @@ class MegaPlan:
             fin = start + t["cost"]
             free[best] = fin
             lists[best].append(ti)
+            prev_cta = best
             sc, _tot, sf, _sm = t["sig"]
             if sc >= 0:
                 cnt_done[sc] = max(cnt_done.get(sc, 0.0), fin)
@@ -402,7 +453,7 @@ class MegaPlan:
                 t = self.task_dicts[ti]
                 r = arr[c, j]
                 for k in ("type", "flags", "m0", "n0", "M", "N", "num_kb", "block_n", "ld_mask", "ld_out", "ld_f32", "ld_target",
-                          "bias", "out_f32", "colsum", "labels", "loss_scale", "seg", "e0", "len", "n_part", "part_off", "part_stride"):
+                          "bias", "out_f32", "colsum", "labels", "loss_scale", "seg", "e0", "len", "n_part", "part_off", "part_stride", "ep_c0", "ep_cols"):
                     r[k] = t[k]
                 for k in ("tmap_a", "tmap_b", "mask", "out_bf16", "loss_slot"):
                     r[k] = t[k]
@@ -433,7 +484,7 @@ class MegaPlan:
         for k in ("flags", "grad", "param", "wbf16"):
             table += list(pt[k]) + [0] * (8 - len(pt[k]))
         self.d_peers = torch.tensor(table, dtype=torch.int64).view(torch.uint8).to(dev)
-        self.d_counters = torch.zeros(max(64, self.n_counters), dtype=torch.int32, device=dev)
+        self.d_counters = torch.zeros(max(64, self.n_counters) * CNT_STRIDE, dtype=torch.int32, device=dev)
         self.d_error = torch.zeros(4, dtype=torch.int32, device=dev)
         mc = pt.get("mc", {}) if W > 1 else {}
         s = self.spec
@@ -503,6 +554,7 @@ class MegaEmulator:
                     self.reg.add(mp.dz[l][p])
         self.counters = [np.zeros(mp.n_counters, dtype=np.int64) for mp in plans]
         self.state = [dict(stopped=False, es_seeded=False, es_best=0.0, es_bad=0, step=0, iter=0, losses=[]) for _ in plans]
+        self.chain_smem: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def _tile_operand(self, spec: TmapSpec, mn: bool, r0: int, k_off: int, width: int, kp: int) -> torch.Tensor:
         """[width, kp] fp32 operand tile with zero fill outside the tensor (what TMA delivers)."""
@@ -574,20 +626,26 @@ class MegaEmulator:
             widx = (w_off + (torch.arange(m0, m0 + rows)[:, None] * w_ld + torch.arange(n0, n0 + cols)[None, :])).reshape(-1)
             fu.wbf16[widx] = p.to(fu.wbf16.dtype)
 
-    def _gemm(self, ri: int, t, par: int, win_off: int, step1: int = 0) -> None:
+    def _gemm(self, ri: int, t, par: int, win_off: int, step1: int = 0, cta: int = 0) -> None:
         mp = self.plans[ri]
         fl, bn, kp = int(t["flags"]), int(t["block_n"]), int(t["num_kb"]) * 64
         m0, n0, M, N = int(t["m0"]), int(t["n0"]), int(t["M"]), int(t["N"])
         sa, sb = mp.tmap_specs[int(t["tmap_a"][par])], mp.tmap_specs[int(t["tmap_b"][par])]
-        if fl & F_A_MN:
+        quiet = bool(fl & F_QUIET)
+        if fl & F_CHAIN_TAIL:                               # A = what the head copy before it left in the CTA's shared memory
+            A = self.chain_smem.pop((ri, cta))[:, :kp]
+        elif fl & F_A_MN:
             A = self._tile_operand(sa, True, m0, 0, 128, kp)
         else:
             A = self._tile_operand(sa, False, m0 + (win_off if (fl & F_A_WIN) else 0), 0, 128, kp)
         Bm = self._tile_operand(sb, bool(fl & F_B_MN), n0, win_off if (fl & F_B_WIN) else 0, bn, kp)
         acc = A @ Bm.t()                                    # [128, bn]
         rows = max(0, min(128, M - m0))
-        cols = max(0, min(bn, N - n0))
-        acc = acc[:rows, :cols].clone()
+        w0 = int(t["ep_c0"])
+        wc = int(t["ep_cols"]) or bn                       # epilogue window: this task drains columns [w0, w0 + wc) of the tile
+        n0 = n0 + w0
+        cols = max(0, min(wc, N - n0))
+        acc = acc[:rows, w0: w0 + cols].clone()
         if fl & F_BIAS:
             acc += self.reg.view1d(int(t["bias"]), N)[n0: n0 + cols].to(torch.float32)
         if fl & F_RELU:
@@ -604,12 +662,20 @@ class MegaEmulator:
             sm = torch.softmax(acc, dim=1)
             sm[torch.arange(rows), y] -= 1.0
             acc = sm * float(t["loss_scale"])
-            self.reg.view1d(int(t["loss_slot"][par]), 1)[0] = li
+            if not quiet:
+                self.reg.view1d(int(t["loss_slot"][par]), 1)[0] = li
         elif fl & F_LOSS_MSE:
             tgt = self.reg.view2d(int(t["labels"]), m0 + lbl_off + rows, N, int(t["ld_target"]))[m0 + lbl_off:, :cols]
             dlt = acc - tgt.to(torch.float32)
-            self.reg.view1d(int(t["loss_slot"][par]), 1)[0] = (dlt * dlt).sum() * float(t["loss_scale"])
+            if not quiet:
+                self.reg.view1d(int(t["loss_slot"][par]), 1)[0] = (dlt * dlt).sum() * float(t["loss_scale"])
             acc = 2.0 * dlt * float(t["loss_scale"])
+        if fl & F_CHAIN_HEAD:
+            buf = torch.zeros(128, 64, dtype=torch.float32)
+            buf[:rows, :cols] = acc.to(mp.plan.act_dtype).to(torch.float32)
+            self.chain_smem[(ri, cta)] = buf
+        if quiet:
+            return
         if fl & F_OUT_BF16:
             out = self.reg.view2d(int(t["out_bf16"][par]), M, N, int(t["ld_out"]))
             out[m0: m0 + rows, n0: n0 + cols] = acc.to(out.dtype)
@@ -715,7 +781,7 @@ class MegaEmulator:
                 win_off = (it % mp.window[0]) * mp.window[1] if mp.window else 0
                 ty = int(t["type"])
                 if ty == MS_GEMM:
-                    self._gemm(ri, t, par, win_off, step0 + s + 1)
+                    self._gemm(ri, t, par, win_off, step0 + s + 1, c)
                 elif ty == MS_UPDATE:
                     self._update(ri, t, step0 + s + 1)
                 elif ty == MS_DECIDE:

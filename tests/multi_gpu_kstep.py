@@ -37,11 +37,11 @@ def main():
     Wt = np.random.default_rng(99).normal(size=(784, 10)).astype(np.float32)
     Y = (X @ Wt).argmax(1).astype(np.float32).reshape(-1, 1)
 
-    def fit(mega, **kw):
+    def fit(mega, opt=torch.optim.Adam, opt_kw=None, **kw):
         os.environ["SPARKTORCH_MEGA"] = "1" if mega else "0"
         torch.manual_seed(1234 + rank)            # deliberately different init per rank: rank 0 must win
         cfg = TrainConfig(device="cuda", seed=5, engine="fused", **kw)
-        return train_partition(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 2e-3}, X, Y, cfg, dev)
+        return train_partition(rank, world, mnist_dnn(), nn.CrossEntropyLoss(), opt, opt_kw or {"lr": 2e-3}, X, Y, cfg, dev)
 
     def all_equal(t, what):
         got = [torch.zeros_like(t) for _ in range(world)]
@@ -62,11 +62,15 @@ def main():
     tb = np.array(b.history["train_loss"])
     np.testing.assert_allclose(tl[:40], tb[:40], rtol=2e-2, atol=2e-3)      # same math: bf16 rounding only, before Adam amplifies it
     assert abs(tl[-10:].mean() - tb[-10:].mean()) < 0.5 * max(tl[-10:].mean(), tb[-10:].mean()) + 0.02
-    a20, b20 = fit(True, iters=20, mini_batch=256, sampling="sweep"), fit(False, iters=20, mini_batch=256, sampling="sweep")
+    # parameters after 20 steps against the kernel-per-op engine.  SGD with momentum: the update is linear in the gradient, so the
+    # two kernel sets may differ by their bf16 rounding only (Adam turns a rounding-level sign flip of a near-zero gradient into a
+    # full +-lr step, which says nothing about the kernels - measured at 8 GPUs: max |diff| 0.06 after 20 Adam steps, same losses)
+    sgd = dict(opt=torch.optim.SGD, opt_kw={"lr": 0.05, "momentum": 0.9})
+    a20, b20 = fit(True, iters=20, mini_batch=256, sampling="sweep", **sgd), fit(False, iters=20, mini_batch=256, sampling="sweep", **sgd)
     if rank == 0:
-        for k in a20.state_dict:             # 20 steps: before Adam has amplified the bf16 rounding differences of the two kernel sets
+        for k in a20.state_dict:
             d = (a20.state_dict[k] - b20.state_dict[k]).abs()
-            assert (d < 4e-3).float().mean().item() > 0.9 and float(d.max()) < 0.1, (k, float(d.max()), (d < 4e-3).float().mean().item())
+            assert (d < 4e-3).float().mean().item() > 0.98 and float(d.max()) < 0.03, (k, float(d.max()), (d < 4e-3).float().mean().item())
         print(f"kstep sync ok: loss {tl[0]:.3f}->{tl[-1]:.3f}; {h['step_kernel']}; comm {h['comm']}; "
               f"step {1e3 * h['window_ms']['device_ms'] / 100:.1f} us (legacy {1e6 * b.history['loop_seconds'] / 160:.1f} us wall)", flush=True)
     # bit-identical replicas: every rank checksums ITS copy of the parameters (the plan's arena is gone, so re-fit briefly and

@@ -316,7 +316,7 @@ def _updater(C, spec, numel, grad, param, wb, segs_rows, patience=-1, zero=True,
     mail = torch.zeros(4, dtype=torch.int32).pin_memory()
     up = C.Updater(1, 0, [grad.data_ptr()], [param.data_ptr()], [wb.data_ptr()] if wb is not None else [], [], 0, m, v,
                    state, hist, mail.data_ptr(), segs, numel, TAIL, spec.kind_id, spec.lr, spec.beta1, spec.beta2, spec.eps,
-                   spec.weight_decay, spec.momentum, spec.dampening, spec.nesterov, spec.maximize, patience, zero, 0, 0)
+                   spec.weight_decay, spec.momentum, spec.dampening, spec.nesterov, spec.maximize, patience, zero, 0, 0, 0, 0)
     return up, state, hist, mail, (m, v, segs)
 
 
