@@ -786,9 +786,11 @@ ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p
       acc[j] = 2.f * dlt * t->loss_scale;
     }
   }
+  if (!(flags & MS_QUIET)) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
-  if (lane == 0) sh->loss_w[q] = li * t->loss_scale;
+    for (int o = 16; o; o >>= 1) li += __shfl_xor_sync(0xffffffffu, li, o);
+    if (lane == 0) sh->loss_w[q] = li * t->loss_scale;
+  }
   // dZ_L (bf16): whole 8-column groups up to the pitch (a multiple of 8); columns >= N inside them are written as zeros
   {
     const bool to_global = row_ok && !(flags & MS_QUIET);
@@ -810,7 +812,7 @@ ST_DEVINL void ms_epilogue_loss(const MsTask* t, MsShared* sh, const MsParams& p
       if (lane == 0) mbar_arrive(&sh->chain_bar);
     }
   }
-  if (flags & MS_COLSUM) {
+  if ((flags & MS_COLSUM) && !(flags & MS_QUIET)) {
     // butterfly over the 32 rows of the warp: afterwards lane L holds the sum of column (L mod NC)
     float v[NC];
 #pragma unroll
@@ -1000,19 +1002,23 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           tma_prefetch_desc(mb);
         }
         __syncwarp();
-        // -- early: what the B operand (weights / the resident batch) needs, then B for the first `pre` k-blocks
+        // -- early: what the early operand needs (B: weights / the resident batch; MS_EARLY_A tiles: nothing - their A is the input
+        //    batch), then that operand for the first `pre` k-blocks
         ms_wait_warp(t, ti, p, epoch, lane, 1);
         fence_proxy_async_all();
         if (stamp && elect_one()) prof[ti * 8 + 1] = (long long)globaltimer_ns();
+        const bool early_a = (flags & MS_EARLY_A) != 0;           // (K-major A only: the batch window of the first layer)
         for (int i = 0; i < pre; ++i) {
           const uint32_t kk = kbc + uint32_t(i);
           const uint32_t st_ = kk & (MS_STAGES - 1);
           ms_mbar_wait(&sh->empty_bar[st_], ((kk / MS_STAGES) & 1) ^ 1, p, 10);
           if (elect_one()) {
-            uint8_t* sb = smem + st_ * MS_STAGE_BYTES + MS_A_BYTES;
-            mbar_arrive_expect_tx(&sh->full_bar[st_], tx);
+            uint8_t* sa = smem + st_ * MS_STAGE_BYTES;
+            uint8_t* sb = sa + MS_A_BYTES;
+            mbar_arrive_expect_tx(&sh->full_bar[st_], tx);           // both operands' bytes: the stage completes with the second one
             const int k0 = i * MS_BLOCK_K;
-            if (b_mn) tma_load_2d(sb, mb, &sh->full_bar[st_], n0, k0 + b_k_off);
+            if (early_a) tma_load_2d(sa, ma, &sh->full_bar[st_], k0, m0 + a_row_off);
+            else if (b_mn) tma_load_2d(sb, mb, &sh->full_bar[st_], n0, k0 + b_k_off);
             else tma_load_2d(sb, mb, &sh->full_bar[st_], k0, n0);
             if (stamp && prof_kb && i < 16) prof_kb[ti * 64 + i * 4 + 0] = (long long)globaltimer_ns();
           }
@@ -1029,12 +1035,12 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
             uint8_t* sa = smem + st_ * MS_STAGE_BYTES;
             uint8_t* sb = sa + MS_A_BYTES;
             const int k0 = i * MS_BLOCK_K;
-            if (i >= pre) {
-              mbar_arrive_expect_tx(&sh->full_bar[st_], tx);
+            if (i >= pre) mbar_arrive_expect_tx(&sh->full_bar[st_], tx);
+            if (i >= pre || early_a) {
               if (b_mn) tma_load_2d(sb, mb, &sh->full_bar[st_], n0, k0 + b_k_off);
               else tma_load_2d(sb, mb, &sh->full_bar[st_], k0, n0);
             }
-            if (chain_tail) {
+            if (chain_tail || (early_a && i < pre)) {
             } else if (a_mn) {
               tma_load_2d(sa, ma, &sh->full_bar[st_], m0, k0);
               tma_load_2d(sa + MS_BLOCK_K * 128, ma, &sh->full_bar[st_], m0 + 64, k0);
@@ -1121,16 +1127,18 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mlp_step_kernel(const __grid_co
           // The epilogue warps acquire the task's dependencies themselves (same polls as the producer warp, concurrently):
           // the bias (published by last step's update), the ReLU mask (this step's forward) and the early-stop decision
           // may then be fetched while the main loop runs, instead of after the accumulator is complete.
-          if (flags & (MS_BIAS | MS_MASK | MS_FUSED_OPT)) {
+          // (a chained tail needs neither: its mask is the activation its head copy - the task before it on this CTA - waited for)
+          if ((flags & (MS_BIAS | MS_MASK | MS_FUSED_OPT)) && !(flags & MS_CHAIN_TAIL)) {
             if (warp == 2) {
               ms_wait_warp(t, ti, p, epoch, lane, -1);
               if (flags & MS_FUSED_OPT) ms_fetch_decision(sh, p, ti, epoch, lane);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");
           }
-          if ((flags & MS_BIAS) && et < bn)
-            sh->bias[et] = (n0 + et < N) ? ld_cg_f32(reinterpret_cast<const float*>(t->bias) + n0 + et) : 0.f;
-          asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");
+          if (flags & MS_BIAS) {
+            if (et < bn) sh->bias[et] = (n0 + et < N) ? ld_cg_f32(reinterpret_cast<const float*>(t->bias) + n0 + et) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(MS_EPI_THREADS) : "memory");
+          }
           const uint32_t tacc = tmem_base + (uint32_t(q * 32) << 16) + as * MS_ACC_COLS;
           long long* slot5 = (stamp && et == 0) ? &prof[ti * 8 + 5] : nullptr;
           if (flags & (MS_LOSS_CE | MS_LOSS_MSE)) {

@@ -37,6 +37,8 @@ enum MsFlags : int32_t {
   MS_CHAIN_HEAD = 1 << 14, // head tile whose epilogue also writes dZ_L (bf16, 128B-swizzled K-major) into the chain buffer
   MS_QUIET = 1 << 15,      // redundant copy of a head tile: nothing is stored to global memory, nothing is signalled
   MS_CHAIN_TAIL = 1 << 16, // A operand = the chain buffer (no TMA load of A)
+  MS_EARLY_A = 1 << 17,    // the A operand is the one without same-step dependencies (the input batch of the first layer): it is
+                           // loaded while the task still waits for its weights, B follows once they are published
 };
 constexpr int MS_CNT_STRIDE = 32;        // one dependency counter per 128-byte line (words): polls of different counters never share a line
 

@@ -35,7 +35,7 @@ MS_MAX_FLAGS = 64
 MS_GEMM, MS_UPDATE, MS_DECIDE = 1, 2, 3
 F_A_MN, F_B_MN, F_RELU, F_A_WIN, F_B_WIN, F_BIAS, F_MASK = 1, 2, 4, 8, 16, 32, 64
 F_OUT_BF16, F_OUT_F32, F_COLSUM, F_LOSS_CE, F_LOSS_MSE, F_LBL_WIN, F_FUSED_OPT = 128, 256, 512, 1024, 2048, 4096, 8192
-F_CHAIN_HEAD, F_QUIET, F_CHAIN_TAIL = 1 << 14, 1 << 15, 1 << 16
+F_CHAIN_HEAD, F_QUIET, F_CHAIN_TAIL, F_EARLY_A = 1 << 14, 1 << 15, 1 << 16, 1 << 17
 CNT_STRIDE = 32            # words between dependency counters on the device (MS_CNT_STRIDE in csrc/mlp_step.h)
 
 # mirrors struct MsTask (csrc/mlp_step.h), 256 bytes
@@ -201,6 +201,8 @@ class MegaPlan:
         # dZ_L to the dgrad MMA through shared memory; the separate head phase (and its signal/wait hop) disappears
         chain = (os.environ.get("SPARKTORCH_MEGA_CHAIN", "1") == "1" and L >= 2 and d[L] <= 32 and not fused_opt)
         self.chain = chain
+        # first layer: the batch (A) has no dependency inside the step, the weights (B) have - load A while waiting for them
+        early_a = os.environ.get("SPARKTORCH_MEGA_EARLY_A", "1") == "1"
         wg_tiles = {l: _cdiv(d[l], 128) * sum(len([c for c in range(0, 64, 64 // split) if d[l - 1] - nt * 64 - c > 0])
                                               for nt in range(_cdiv(d[l - 1], 64))) for l in range(1, L + 1)}
 
@@ -255,19 +257,21 @@ class MegaPlan:
                     src_rows = self.x_src.shape[0] if l == 1 else B
                     if l == L and chain:
                         assert ntl == 1
-                        tasks_before = len(tasks)
                     t = new_task(type=MS_GEMM, m0=mt * 128, n0=nt * bn, M=B, N=d[l], num_kb=nkb, block_n=bn,
                                  tmap_a=[self._tmap(src_of(l - 1, p), src_rows, K, 128) for p in range(2)],
                                  tmap_b=[self._tmap(Wb, d[l], K, bn)] * 2,
                                  bias=_addr(plan.bias[l - 1]) if has_bias[l - 1] else 0, cost=1.2 + 0.15 * nkb, group=f"F{l}")
                     if l == 1 and windowed:
                         fl |= F_A_WIN
+                    if l == 1 and early_a:
+                        fl |= F_EARLY_A
                     w = []
                     if l > 1:
                         w.append(w_cnt(c_act(l - 1), n_f_tiles[l - 1]))
-                    w.append(w_pub(seg_of_w[l - 1]))
+                    b_early = not (l == 1 and early_a)      # early-A tiles: the weights are the late operand
+                    w.append(w_pub(seg_of_w[l - 1], early=b_early))
                     if has_bias[l - 1]:
-                        w.append(w_pub(seg_of_b[l - 1]))
+                        w.append(w_pub(seg_of_b[l - 1], early=b_early))
                     t["wait"] = w
                     if l < L:
                         fl |= F_OUT_BF16
@@ -288,16 +292,14 @@ class MegaPlan:
                         # the head's tiles complete dZ_L, db_L and the loss of this rank: flag gr(b_L) doubles as "loss ready"
                         t["sig"] = [c_dz(L), n_f_tiles[L], -1 if single else f_dz(L), all_mask]
                     t["flags"] = fl
-                    if l == L and chain:        # not a task of its own: the template of the head copies of m-tile mt
-                        del tasks[tasks_before:]
+                    if l == L and chain:        # also the template of the (quiet) head copies in front of the dgrad tiles of m-tile mt
                         head_of[mt] = t
         self.loss_flag = f_dz(L)
         # ---------------------------------------------------------------- decision
         def decide_task():
             new_task(type=MS_DECIDE, wait=[w_cnt(c_dz(L), n_f_tiles[L]) if single else w_flag(self.loss_flag, 0, all_mask)], cost=0.5, group="D")
 
-        if not chain:           # (chained head: created behind the head copies it waits for - list order is a topological order)
-            decide_task()
+        decide_task()
         # ---------------------------------------------------------------- backward, last layer first
         n_dz_tiles = [0] * (L + 1)
         n_dz_tiles[L] = n_f_tiles[L]
@@ -335,12 +337,12 @@ class MegaPlan:
                     for j, (nt, (wc0, wcn)) in enumerate([(nt_, w_) for nt_ in range(ntl) for w_ in wins(nt_, d[l - 1])]):
                         fl = F_B_MN | F_OUT_BF16
                         if chained:
-                            # the head copy that feeds this tile; the first one of the m-tile is the one that stores dZ_L / db_L /
-                            # the loss partial and signals them, the others keep everything on chip
+                            # the head copy that feeds this tile keeps everything on chip; dZ_L / db_L / the loss partial for the
+                            # weight gradient, the bias update and the decision come from the regular head tiles of the forward
+                            # pass (their stores and signal are then off the critical path of this tile)
                             h = dict(head_of[mt])
-                            h["flags"] |= F_CHAIN_HEAD | (F_QUIET if j else 0)
-                            if j:
-                                h["sig"] = [-1, 0, -1, 0]
+                            h["flags"] |= F_CHAIN_HEAD | F_QUIET
+                            h["sig"] = [-1, 0, -1, 0]
                             h["group"] = f"H{l}"
                             tasks.append(h)
                             fl |= F_CHAIN_TAIL
@@ -360,8 +362,6 @@ class MegaPlan:
                             t["colsum"] = colsum_ptr(l - 1, mt)
                         t["sig"] = [c_dz(l - 1), n_dz_tiles[l - 1], -1 if single else f_dz(l - 1), all_mask]
                         t["flags"] = fl
-            if chained:
-                decide_task()
             if has_bias[l - 1] and chained:       # (after the tiles it waits for: every CTA's list stays a topological order)
                 bias_update()
             # wgrad: dW_l[d_l, d_{l-1}] = dZ_l^T A_{l-1}   (both operands MN-major, reduction over the batch)

@@ -107,7 +107,7 @@ def test_early_stop_random_sampling_and_streaming_paths():
     a = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, sampling="sweep")
     b = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, streaming=True)
     c = _fit(copy.deepcopy(net), nn.CrossEntropyLoss(), torch.optim.Adam, {"lr": 1e-3}, X, Y, iters=24, mini_batch=256, sampling="random")
-    assert b.history["streaming"] and b.history["step_kernel"]["steps_per_launch"] == 1
+    assert b.history["streaming"] and b.history["step_kernel"]["steps_per_launch"] == 4      # SPARKTORCH_STREAM_STEPS
     np.testing.assert_allclose(a.history["train_loss"], b.history["train_loss"], rtol=1e-3, atol=1e-4)
     assert c.history["gpu_launches_per_step"] == 2 and c.history["train_loss"][-1] < c.history["train_loss"][0]
 
