@@ -682,6 +682,15 @@ int64_t flag_words() { return st::AR_FLAG_WORDS; }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "sparktorch_b200 native kernels (sm_100a)";
+  m.def("gemm_bf16_2cta", [](const Tensor& A, const Tensor& B, Tensor& Cout, const c10::optional<Tensor>& bias, double alpha, bool relu) {
+    TORCH_CHECK(A.is_cuda() && B.is_cuda() && Cout.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16 &&
+                Cout.scalar_type() == at::kBFloat16 && A.dim() == 2 && B.dim() == 2 && Cout.dim() == 2);
+    TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && Cout.stride(1) == 1 && A.size(1) == B.size(1) && Cout.size(0) == A.size(0) && Cout.size(1) == B.size(0));
+    const float* bp = nullptr;
+    if (bias.has_value()) { TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kFloat && bias->numel() >= B.size(0)); bp = bias->data_ptr<float>(); }
+    return st::gemm_bf16_2cta(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cout.data_ptr(), Cout.stride(0), int(A.size(0)), int(B.size(0)),
+                              int(A.size(1)), bp, float(alpha), relu ? 1 : 0, cur_stream());
+  }, "bf16 GEMM on CTA pairs (cta_group::2): C = act(alpha A B^T + bias); returns 0, or -2 when the shape is left to gemm_bf16");
   m.def("gemm_bf16", &gemm_bf16, "tcgen05 bf16 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"),
         py::arg("b_mn"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("alpha") = 1.0, py::arg("bias") = py::none(),
         py::arg("relu") = false, py::arg("mask_src") = py::none(), py::arg("out_bf16") = py::none(),

@@ -25,7 +25,7 @@ BUILD = os.path.join(HERE, "_build")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["gemm_sm100.cu", "loss.cu", "data.cu", "comm_ar.cu", "comm_hw.cu", "conv.cu", "norm.cu", "mlp_step.cu"]
+CU_SOURCES = ["gemm_sm100.cu", "gemm2cta_sm100.cu", "loss.cu", "data.cu", "comm_ar.cu", "comm_hw.cu", "conv.cu", "norm.cu", "mlp_step.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 MODULE = "_C"
 

@@ -75,6 +75,10 @@ struct GemmWindow {
 
 int gemm_pick_block_n(int M, int N, int b_mn);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+// C = act(alpha * A B^T + bias) on CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles); -2: shape not handled (gemm2cta_sm100.cu)
+int gemm_bf16_2cta(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int M, int N, int K, const float* bias,
+                   float alpha, int relu, cudaStream_t stream);
 int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue* ep, const GemmWindow* win, int64_t a_rows_total, int64_t b_rows_total, int block_n,
               int split_k, cudaStream_t stream, const GemmPeerB* peer = nullptr);
