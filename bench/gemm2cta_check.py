@@ -57,7 +57,11 @@ for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 4096), (16384, 4096, 1024), (
     rec = {"M": M, "N": N, "K": K}
     rec["pair_ms"] = timed(lambda i: C.gemm_bf16_2cta(As[i % nbuf], Bs[i % nbuf], o, None, 1.0, False))
     C.set_persistent_mode(1)
+    if hasattr(C, "set_pair_mode"):
+        C.set_pair_mode(0)
     rec["single_ms"] = timed(lambda i: C.gemm_bf16(As[i % nbuf], False, Bs[i % nbuf], False, M, N, K, 1.0, None, False, None, o, None, None, None, False, None, 256, 1))
+    if hasattr(C, "set_pair_mode"):
+        C.set_pair_mode(1)
     rec["cublas_ms"] = timed(lambda i: torch.matmul(As[i % nbuf], Bs[i % nbuf].t(), out=o))
     for k in ("pair", "single", "cublas"):
         rec[k + "_tflops"] = fl / rec[k + "_ms"]

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparktorch_b200.ops import native  # noqa: E402
 
 C = native.load(required=True)
+C.set_pair_mode(0)         # this script measures the single-CTA kernels; bench/gemm2cta_check.py measures the CTA-pair kernel
 dev = torch.device("cuda", 0)
 PEAK = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"bf16_tflops": 1590.0}
 out = []

@@ -673,6 +673,7 @@ class GraphRunner {
 };
 
 void set_persistent_mode(int64_t m) { st::g_persistent_mode = int(m); }
+void set_pair_mode(int64_t m) { st::g_pair_mode = int(m); }
 void set_pdl(bool on) { st::g_use_pdl = on; }
 bool get_pdl() { return st::g_use_pdl; }
 int64_t step_state_bytes() { return int64_t(sizeof(st::StepState)); }
@@ -738,6 +739,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("step_state_bytes", &step_state_bytes);
   m.def("set_pdl", &set_pdl);
   m.def("set_persistent_mode", &set_persistent_mode);
+  m.def("set_pair_mode", &set_pair_mode, "0: gemm_bf16 never hands big plain products to the CTA-pair kernel");
   m.def("get_pdl", &get_pdl);
   m.def("flag_words", &flag_words);
   py::class_<Updater>(m, "Updater")

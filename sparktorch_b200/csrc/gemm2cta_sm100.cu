@@ -10,7 +10,10 @@
 //
 //   warp 0      TMA producer (both CTAs; `.cta_group::2` loads complete on the LEADER's mbarrier)
 //   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs
-//   warps 2-9   epilogue: tcgen05.ld -> bias / ReLU -> bf16 -> 16-byte global stores; arrive on the leader's "TMEM free" barrier
+//   warps 2-9   epilogue: tcgen05.ld -> bias / ReLU -> bf16 -> swizzled shared-memory staging -> TMA store (full 128-byte lines,
+//               ragged edges clipped by the tensor map); arrive on the leader's "TMEM free" barrier once TMEM has been read
+// Tiles are walked in groups of 8 tile rows (all pairs of a wave then share ~8 A panels and ~9 B panels: the wave's operands
+// fit the L2; a plain row-major walk streams all of A from HBM once per tile column).
 //
 // Replaces the cuBLAS GEMMs behind every Linear / Conv2d forward of the reference (torch ops called at
 // /root/reference/sparktorch/distributed.py:150,176).
@@ -38,7 +41,11 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_THREADS = 320;
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_MISC = 2048;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_MISC + 1024;
+constexpr int G2_CSTAGE_BYTES = 32 * 128;                    // per epilogue warp: 32 rows x 64 bf16 columns
+constexpr int G2_CSTAGE_OFF = G2_STAGES * G2_STAGE_BYTES;    // 1024-byte aligned
+constexpr int G2_MISC_OFF = G2_CSTAGE_OFF + G2_EPI_WARPS * G2_CSTAGE_BYTES;
+constexpr int G2_SMEM = G2_MISC_OFF + G2_MISC + 1024;
+constexpr int G2_GROUP_M = 8;                                // tile rows per rasterisation group
 constexpr uint32_t G2_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: "the same object in CTA 0 of the pair"
 
 struct G2Shared {
@@ -104,6 +111,26 @@ ST_DEVINL void g2_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+ST_DEVINL void tma_store_2d(const void* desc, const void* smem_src, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+ST_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+ST_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+ST_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// tile t of the walk -> (tile row, tile column): groups of G2_GROUP_M tile rows, column-major inside a group
+ST_DEVINL void g2_tile(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = G2_GROUP_M * tiles_n;
+  const int gidx = t / per_group;
+  const int first_m = gidx * G2_GROUP_M;
+  const int rows = min(G2_GROUP_M, tiles_m - first_m);
+  const int r = t - gidx * per_group;
+  tm = first_m + r % rows;
+  tn = r / rows;
+}
+
 struct G2Args {
   __nv_bfloat16* C;
   int64_t ldc;
@@ -115,10 +142,11 @@ struct G2Args {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const G2Args g) {
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_c, const G2Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  G2Shared* sh = reinterpret_cast<G2Shared*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  G2Shared* sh = reinterpret_cast<G2Shared*>(smem + G2_MISC_OFF);
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -131,6 +159,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&sh->full_bar[s], 1);
       mbar_init(&sh->empty_bar[s], 1);
@@ -155,8 +184,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ===================== TMA producer (both CTAs) =====================
     uint32_t kbc = 0;
     for (int t = pair; t < n_tiles; t += n_pairs) {
-      const int m0 = (t % g.tiles_m) * (2 * G2_BM) + int(rank) * G2_BM;
-      const int n0 = (t / g.tiles_m) * G2_BN + int(rank) * G2_BN_HALF;
+      int tm, tn;
+      g2_tile(t, g.tiles_m, g.tiles_n, tm, tn);
+      const int m0 = tm * (2 * G2_BM) + int(rank) * G2_BM;
+      const int n0 = tn * G2_BN + int(rank) * G2_BN_HALF;
       for (int i = 0; i < num_kb; ++i, ++kbc) {
         const uint32_t s = kbc % G2_STAGES;
         g2_wait(&sh->empty_bar[s], ((kbc / G2_STAGES) & 1) ^ 1);
@@ -200,48 +231,56 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ===================== epilogue (both CTAs, 8 warps: TMEM lane quadrant x column half) =====================
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    uint8_t* cst = smem + G2_CSTAGE_OFF + (warp - 2) * G2_CSTAGE_BYTES;     // this warp's staging tile: 32 rows x 128 B, 128B-swizzled
     uint32_t tc = 0;
     for (int t = pair; t < n_tiles; t += n_pairs, ++tc) {
       const uint32_t as = tc & 1;
-      const int row = (t % g.tiles_m) * (2 * G2_BM) + int(rank) * G2_BM + q * 32 + lane;
-      const int n0 = (t / g.tiles_m) * G2_BN;
-      const bool row_ok = row < g.M;
+      int tm, tn;
+      g2_tile(t, g.tiles_m, g.tiles_n, tm, tn);
+      const int row0 = tm * (2 * G2_BM) + int(rank) * G2_BM + q * 32;       // first row of this warp's 32
+      const int colw = tn * G2_BN + half * (G2_BN / 2);                       // first of this warp's 128 columns
       g2_wait(&sh->tmem_full_bar[as], (tc >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t(q * 32) << 16) + as * G2_BN + half * (G2_BN / 2);
-      __nv_bfloat16* crow = g.C + size_t(row_ok ? row : 0) * g.ldc;
 #pragma unroll 1
-      for (int c = 0; c < G2_BN / 2; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tacc + c, r);
+      for (int c = 0; c < G2_BN / 2; c += 64) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(tacc + c, r0);
+        tmem_ld_32x32(tacc + c + 32, r1);
         tmem_ld_wait();
-        const int col0 = n0 + half * (G2_BN / 2) + c;
-        if (row_ok && col0 < g.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) * g.alpha;
-            if (g.bias != nullptr && col0 + j < g.N) x += __ldg(g.bias + col0 + j);
-            if (g.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
-          }
-          if (col0 + 32 <= g.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack_bf16x2(v[j + 0], v[j + 1]); w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              w.z = pack_bf16x2(v[j + 4], v[j + 5]); w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(crow + col0 + j) = w;
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < g.N; ++j) crow[col0 + j] = __float2bfloat16(v[j]);
-          }
+        if (c + 64 == G2_BN / 2) {            // last TMEM read of this tile: the MMA warp may start the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&sh->tmem_empty_bar[as], 0);
         }
+        const int col0 = colw + c;
+        tma_store_wait_read();                // the previous TMA store has finished reading the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {         // eight 16-byte chunks (8 columns each) of this lane's row
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int jj = 8 * v + j;
+            float y = __uint_as_float(jj < 32 ? r0[jj] : r1[jj - 32]) * g.alpha;
+            if (g.bias != nullptr && col0 + jj < g.N) y += __ldg(g.bias + col0 + jj);
+            if (g.relu) y = fmaxf(y, 0.f);
+            x[j] = y;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]); w.z = pack_bf16x2(x[4], x[5]); w.w = pack_bf16x2(x[6], x[7]);
+          *reinterpret_cast<uint4*>(cst + lane * 128 + ((v ^ (lane & 7)) << 4)) = w;
+        }
+        fence_proxy_async();                  // generic-proxy stores -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && row0 < g.M && col0 < g.N) {
+          tma_store_2d(&tmap_c, cst, col0, row0);     // rows >= M / columns >= N are clipped by the tensor map
+          tma_store_commit();
+        }
+        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&sh->tmem_empty_bar[as], 0);
     }
+    tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -259,8 +298,11 @@ int gemm_bf16_2cta(const void* A, int64_t lda, const void* B, int64_t ldb, void*
                    float alpha, int relu, cudaStream_t stream) {
   if (M < 256 || N < 256 || K < 64 || (lda % 8) || (ldb % 8) || (ldc % 8)) return -2;
   CUtensorMap ta, tb;
+  if ((reinterpret_cast<uintptr_t>(C) & 15) != 0) return -2;
   if (make_tmap_bf16_2d(&ta, A, uint64_t(M), uint64_t(K), uint64_t(lda), G2_BM) != 0) return -3;
   if (make_tmap_bf16_2d(&tb, B, uint64_t(N), uint64_t(K), uint64_t(ldb), G2_BN_HALF) != 0) return -3;
+  CUtensorMap tc;
+  if (make_tmap_bf16_2d(&tc, C, uint64_t(M), uint64_t(N), uint64_t(ldc), 32) != 0) return -3;
   static int n_sm = 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -282,7 +324,7 @@ int gemm_bf16_2cta(const void* A, int64_t lda, const void* B, int64_t ldb, void*
   const int n_tiles = g.tiles_m * g.tiles_n;
   int pairs = n_sm / 2;
   if (pairs > n_tiles) pairs = n_tiles;
-  gemm_bf16_2cta_kernel<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(ta, tb, g);
+  gemm_bf16_2cta_kernel<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(ta, tb, tc, g);
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

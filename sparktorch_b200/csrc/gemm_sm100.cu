@@ -25,6 +25,7 @@ namespace st {
 
 bool g_use_pdl = false;
 int g_persistent_mode = 1;   // 0 never, 1 when tiles > #SMs, 2 always (tests)
+int g_pair_mode = 1;         // 0: never hand big plain products to the CTA-pair kernel (tests / comparisons)
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
@@ -828,6 +829,14 @@ int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, 
   if (b_mn && block_n < 64) block_n = 64;
   if (split_k <= 0) split_k = 1;
   if (split_k > 1 && !ep->atomic_f32) return -3;
+  // Big plain products (forward of wide Linear / im2col'ed convolutions): CTA pairs with tcgen05.mma.cta_group::2 (gemm2cta_sm100.cu)
+  if (g_pair_mode != 0 && !a_mn && !b_mn && peer.world == 0 && win.flags == 0 && split_k == 1 && ep->out_bf16 != nullptr &&
+      ep->mask_src == nullptr && ep->out_t_bf16 == nullptr && ep->out_f32 == nullptr && ep->out_t_f32 == nullptr && ep->colsum == nullptr &&
+      ep->colsumsq == nullptr && ep->loss_kind == 0 && ep->push_world == 0 && ep->prof == nullptr && M >= 512 && N >= 256 && K >= 256 &&
+      int64_t(M) * N >= (int64_t(1) << 20) && (ep->ld_out & 7) == 0) {
+    const int rc2 = gemm_bf16_2cta(A, lda, B, ldb, ep->out_bf16, ep->ld_out, M, N, K, ep->bias, ep->alpha, ep->relu, stream);
+    if (rc2 != -2) return rc2;
+  }
   CUtensorMap ta, tb;
   // windowed operands are described over the whole resident matrix (rows_total), the kernel adds the offset
   const uint64_t a_rows = (win.flags & 1) && a_rows_total > 0 ? uint64_t(a_rows_total) : uint64_t(M);

@@ -8,6 +8,7 @@ namespace st {
 
 extern bool g_use_pdl;   // launch the step kernels with programmatic dependent launch
 extern int g_persistent_mode;   // GEMM: 0 never persistent, 1 auto (tiles > #SMs), 2 always
+extern int g_pair_mode;         // GEMM: 1 (default) big plain products run on CTA pairs (cta_group::2), 0 never
 
 // ---- loss.cu
 int softmax_ce(const float* logits, int64_t ldz, const int32_t* labels, int B, int C, float* loss_slot,

@@ -561,3 +561,29 @@ def test_gemm_persistent_variant(C, a_mn, b_mn, block_n):
     torch.testing.assert_close(o32, ref, rtol=2e-3, atol=0.15)
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=0.2)
     torch.testing.assert_close(cs, ref.sum(0), rtol=2e-2, atol=2.0)
+
+
+@pytest.mark.parametrize("M,N,K,bias,relu", [(256, 256, 64, False, False), (1000, 640, 200, True, True), (2048, 1024, 4096 + 64, True, False),
+                                             (777, 1280, 512, False, True)])
+def test_gemm_cta_pair_variant(C, M, N, K, bias, relu):
+    """tcgen05.mma.cta_group::2 kernel (CTA pairs, 256 x 256 tiles, csrc/gemm2cta_sm100.cu): ragged M / N / K, ring wrap-around
+    (K = 65 k-blocks > 6 stages), both accumulator stages (more tiles than pairs is covered by 2048 x 1024 on a full GPU)."""
+    a, b = _mk(M, K, seed=1), _mk(N, K, seed=2)
+    bv = torch.randn(N, device=dev()) if bias else None
+    out = torch.full((M, _pad8(N)), float("nan"), dtype=torch.bfloat16, device=dev())[:, :N]
+    rc = C.gemm_bf16_2cta(a, b, out, bv, 0.5, relu)
+    torch.cuda.synchronize()
+    assert rc == 0
+    ref = 0.5 * (a.float() @ b.float().t())
+    if bias:
+        ref = ref + bv
+    if relu:
+        ref = ref.clamp_min(0)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2 * math.sqrt(K) / 8 + 1e-2)
+
+
+def test_gemm_cta_pair_declines_small_shapes(C):
+    a, b = _mk(128, 64), _mk(64, 64)
+    out = torch.zeros(128, 64, dtype=torch.bfloat16, device=dev())
+    assert C.gemm_bf16_2cta(a, b, out, None, 1.0, False) == -2
