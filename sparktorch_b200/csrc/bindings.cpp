@@ -503,6 +503,11 @@ class MlpStep {
     p_.n_mt = int(n_mt); p_.loss_off = loss_off; p_.window_rows = window_rows; p_.n_windows = n_windows > 0 ? n_windows : 1;
     p_.error = reinterpret_cast<uint32_t*>(error.data_ptr<int32_t>());
   }
+  // cross-GPU dependencies as counters in the symmetric flag block (wait kind 3); mc_flags_ptr: its multicast alias or 0
+  void set_xcnt(int64_t mc_flags_ptr) {
+    p_.xcnt = 1;
+    p_.mc_flags = reinterpret_cast<uint32_t*>(mc_flags_ptr);
+  }
   void set_prof_kb(const OptT& prof) {
     prof_kb_ = prof;
     if (prof) {
@@ -772,6 +777,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     const OptT&, int64_t, int64_t, double, double, double, double, double, double, double, bool, bool, int64_t,
                     int64_t, int64_t, int64_t, int64_t, int64_t, const Tensor&>())
       .def("set_prof", &MlpStep::set_prof)
+      .def("set_xcnt", &MlpStep::set_xcnt)
       .def("set_prof_kb", &MlpStep::set_prof_kb)
       .def("run", &MlpStep::run)
       .def("run_many", &MlpStep::run_many, py::call_guard<py::gil_scoped_release>())

@@ -179,6 +179,10 @@ ST_DEVINL void ms_wait_warp(const MsTask* t, int ti, const MsParams& p, uint32_t
       target = epoch - uint32_t(t->wait[w].need);      // need = lag: 1 waits for the PREVIOUS step's flag
       ptr = p.flags_local + t->wait[w].idx * 8 + r;
       sys = true;
+    } else if (kind == 3 && r == 0) {
+      target = (epoch - uint32_t(t->wait[w].mask)) * uint32_t(t->wait[w].need);
+      ptr = p.flags_local + MS_XCNT_BASE + t->wait[w].idx * MS_CNT_STRIDE;
+      sys = true;
     }
   }
   const bool any = __any_sync(0xffffffffu, ptr != nullptr);
@@ -209,6 +213,20 @@ ST_DEVINL void ms_signal(const MsTask* t, const MsPeerTable* peers, const MsPara
   if (t->sig_cnt < 0) return;
   if (t->sig_flag < 0) {       // nobody needs the count: release-increment, no round trip
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + t->sig_cnt * MS_CNT_STRIDE), "r"(1u) : "memory");
+    return;
+  }
+  if (p.xcnt) {
+    // every task tells every consumer rank itself: one system-scope fence (this CTA's stores, made visible to this thread by the
+    // block barrier, are ordered before the increments), then relaxed adds - through the switch's multicast when all ranks listen
+    if (p.world > 1) fence_acqrel_sys(); else fence_acqrel_gpu();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p.counters + t->sig_cnt * MS_CNT_STRIDE), "r"(1u) : "memory");
+    const int off = MS_XCNT_BASE + t->sig_flag * MS_CNT_STRIDE;
+    if (p.mc_flags != nullptr && t->sig_mask == (1 << p.world) - 1) {
+      asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.mc_flags + off), "r"(1u) : "memory");
+    } else {
+      for (int r = 0; r < p.world; ++r)
+        if ((t->sig_mask >> r) & 1) asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(peers->flags[r] + off), "r"(1u) : "memory");
+    }
     return;
   }
   const uint32_t old = atom_add_acqrel_gpu(p.counters + t->sig_cnt * MS_CNT_STRIDE, 1u);

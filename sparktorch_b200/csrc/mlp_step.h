@@ -40,9 +40,12 @@ enum MsFlags : int32_t {
   MS_EARLY_A = 1 << 17,    // the A operand is the one without same-step dependencies (the input batch of the first layer): it is
                            // loaded while the task still waits for its weights, B follows once they are published
 };
+constexpr int MS_XCNT_BASE = 1024;       // word offset of the cross-GPU counters inside the symmetric flag block (ids * MS_CNT_STRIDE follow)
 constexpr int MS_CNT_STRIDE = 32;        // one dependency counter per 128-byte line (words): polls of different counters never share a line
 
-struct MsWait {            // kind 0: none; 1: local counter (>= epoch * need); 2: cross-GPU flag `idx` from every rank in `mask` (>= epoch)
+struct MsWait {            // kind 0: none; 1: local counter (>= epoch * need); 2: cross-GPU flag `idx` from every rank in `mask` (>= epoch);
+                           // 3: cross-GPU COUNTER `idx` in this rank's symmetric block (>= (epoch - mask) * need; need = arrivals per
+                           //    step from all ranks): every producer task adds 1 on every consumer rank itself - no last-arriver hop
   int32_t kind, idx, need, mask;
 };
 
@@ -116,6 +119,8 @@ struct MsParams {
   long long* prof;         // optional [grid][MS_MAX_TASKS][8] globaltimer stamps of the last step
   long long* prof_kb;      // optional [grid][MS_MAX_TASKS][16][4]: per k-block B issued, A issued, stage landed (MMA thread), unused
   uint32_t* error;         // [4] device word set before a trap: code, cta, task, epoch
+  int xcnt;                // 1: cross-GPU dependencies are counters (wait kind 3), tasks signal every consumer rank directly
+  uint32_t* mc_flags;      // NVLS multicast alias of the symmetric flag block (null: one red per peer)
 };
 
 int ms_smem_bytes();

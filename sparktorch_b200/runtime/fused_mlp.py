@@ -504,7 +504,7 @@ def try_fused_fit(rank, world, model, criterion, opt_cls, opt_params, X, Y, cfg,
             blk = fu.block
             peers = {k: blk.peer_ptrs(k) for k in ("flags", "grad", "param", "wbf16")}
             if world > 1 and fu.use_multicast:
-                peers["mc"] = {k: blk.multicast_ptr(k) for k in ("grad", "param", "wbf16")}
+                peers["mc"] = {k: blk.multicast_ptr(k) for k in ("grad", "param", "wbf16", "flags")}
             flag_view = blk.view("flags", torch.int32, C.flag_words())
             if windowed:
                 mx, mt_, mwin = src, tgt_src, (windows, Bt)

@@ -37,6 +37,7 @@ F_A_MN, F_B_MN, F_RELU, F_A_WIN, F_B_WIN, F_BIAS, F_MASK = 1, 2, 4, 8, 16, 32, 6
 F_OUT_BF16, F_OUT_F32, F_COLSUM, F_LOSS_CE, F_LOSS_MSE, F_LBL_WIN, F_FUSED_OPT = 128, 256, 512, 1024, 2048, 4096, 8192
 F_CHAIN_HEAD, F_QUIET, F_CHAIN_TAIL, F_EARLY_A = 1 << 14, 1 << 15, 1 << 16, 1 << 17
 CNT_STRIDE = 32            # words between dependency counters on the device (MS_CNT_STRIDE in csrc/mlp_step.h)
+XCNT_BASE = 1024           # word offset of the cross-GPU counters in the symmetric flag block (MS_XCNT_BASE)
 
 # mirrors struct MsTask (csrc/mlp_step.h), 256 bytes
 MS_TASK = np.dtype([
@@ -163,7 +164,16 @@ class MegaPlan:
         def w_cnt(idx, need, lag=0, early=False):
             return [1 | (EARLY if early else 0), idx, need, lag]
 
-        def w_flag(idx, lag, mask, early=False):
+        # cross-GPU dependencies: epoch flags raised by the last arriver of a group of tasks (kind 2), or - SPARKTORCH_MEGA_XCNT=1 -
+        # counters in the consumer's symmetric block that EVERY producer task bumps itself on every consumer rank (kind 3: one
+        # hop less on the exposed W_1 exchange; `arrivals` = increments per step from all ranks together)
+        xcnt = W > 1 and os.environ.get("SPARKTORCH_MEGA_XCNT", "0") == "1"
+        self.xcnt = xcnt
+
+        def w_flag(idx, lag, mask, early=False, arrivals=0):
+            if xcnt:
+                assert arrivals > 0
+                return [3 | (EARLY if early else 0), idx, arrivals, lag]
             return [2 | (EARLY if early else 0), idx, lag, mask]
         # ownership: flat ranges of float4s (ZeRO-1 layout of parallel/p2p.py)
         n4 = numel // 4
@@ -189,6 +199,13 @@ class MegaPlan:
             lo, hi = max(seg_range[sidx][0], self.owned[0]), min(seg_range[sidx][1], self.owned[1])
             return _cdiv(hi - lo, ch) if lo < hi else 0
 
+        def all_chunks(sidx: int) -> int:          # update chunks of segment sidx on all owners together
+            n = 0
+            for r in range(W):
+                lo, hi = max(seg_range[sidx][0], min(numel, per * r)), min(seg_range[sidx][1], min(numel, per * (r + 1)))
+                n += _cdiv(hi - lo, ch) if lo < hi else 0
+            return n
+
         # one GPU: Adam/SGD is applied by the weight-gradient tiles themselves (no update phase for the weights)
         # (opt-in: with thread = weight row the in-place update writes 32-byte pieces of 32 different rows per instruction;
         #  the separate, fully coalesced update chunks are faster for the MNIST-sized layers - profiles/kstep_timeline_*.md)
@@ -212,7 +229,7 @@ class MegaPlan:
                 return w_cnt(c_wg(l), wg_tiles[l], lag=1, early=early)
             if single:
                 return w_cnt(c_upd(sidx), my_chunks(sidx), lag=1, early=early)
-            return w_flag(f_pub(sidx), 1, seg_owner[sidx], early=early)
+            return w_flag(f_pub(sidx), 1, seg_owner[sidx], early=early, arrivals=all_chunks(sidx))
 
         tasks: List[dict] = []
 
@@ -297,7 +314,8 @@ class MegaPlan:
         self.loss_flag = f_dz(L)
         # ---------------------------------------------------------------- decision
         def decide_task():
-            new_task(type=MS_DECIDE, wait=[w_cnt(c_dz(L), n_f_tiles[L]) if single else w_flag(self.loss_flag, 0, all_mask)], cost=0.5, group="D")
+            new_task(type=MS_DECIDE, wait=[w_cnt(c_dz(L), n_f_tiles[L]) if single else w_flag(self.loss_flag, 0, all_mask, arrivals=W * n_f_tiles[L])],
+                     cost=0.5, group="D")
 
         decide_task()
         # ---------------------------------------------------------------- backward, last layer first
@@ -314,7 +332,7 @@ class MegaPlan:
                          cost=1.5, group=f"U{s}")
 
         def w_dz(l):       # "dZ_l (and db_l) of this step complete on every replica"
-            return w_cnt(c_dz(l), n_dz_tiles[l]) if single else w_flag(f_dz(l), 0, all_mask)
+            return w_cnt(c_dz(l), n_dz_tiles[l]) if single else w_flag(f_dz(l), 0, all_mask, arrivals=W * n_dz_tiles[l])
 
         # the 64-wide backward tile is run by `split` CTAs that drain one window of its columns each (epilogue time ~ columns per thread)
         wins = lambda nt_, N_: [(c, min(64 // split, N_ - nt_ * 64 - c)) for c in range(0, 64, 64 // split) if N_ - nt_ * 64 - c > 0]   # noqa: E731
@@ -387,7 +405,7 @@ class MegaPlan:
             # W_l may only be overwritten (on EVERY replica: the owner publishes everywhere) once every replica's dgrad of
             # this step has read it: dZ_{l-1} complete  <=>  the B_l tiles are done
             if not fused_opt:
-                w_gw = w_cnt(c_wg(l), n_g) if single else w_flag(f_gw(l), 0, all_mask)
+                w_gw = w_cnt(c_wg(l), n_g) if single else w_flag(f_gw(l), 0, all_mask, arrivals=W * n_g)
                 update_tasks(sw, [w_gw] + ([w_dz(l - 1)] if l > 1 else []), 1, 0)
         self.task_dicts = tasks
         if not self._place():
@@ -417,6 +435,8 @@ class MegaPlan:
                     ready = max(ready, cnt_done.get(idx, 0.0))
                 elif (k & 15) == 2 and need == 0:
                     ready = max(ready, flag_done.get(idx, 0.0) + (1.5 if self.world > 1 else 0.0))
+                elif (k & 15) == 3 and m == 0:
+                    ready = max(ready, flag_done.get(idx, 0.0) + 1.0)
             if t.get("after_prev"):
                 best = prev_cta                 # second half of a chained pair: same CTA, right behind the head copy
             elif t["type"] == MS_DECIDE:
@@ -494,6 +514,8 @@ class MegaPlan:
             fu.m, fu.v, self.shard_lo, fu._segs, fu.state, fu.loss_hist, fu.mailbox.data_ptr(), s.kind_id, s.lr, s.beta1,
             s.beta2, s.eps, s.weight_decay, s.momentum, s.dampening, s.nesterov, s.maximize, self.patience, self.decide_cnt,
             self.n_mt, self.loss_off, self.window[1] if self.window else 0, self.window[0] if self.window else 1, self.d_error)
+        if self.xcnt:
+            self.native.set_xcnt(int(mc.get("flags", 0)))
         return self.native
 
     def describe(self) -> dict:
@@ -583,6 +605,8 @@ class MegaEmulator:
                 for r in range(self.W):
                     if (mask >> r) & 1 and int(fl[idx * 8 + r]) < epoch - need:
                         return False
+            if k == 3 and int(mp.flags[XCNT_BASE + idx * CNT_STRIDE]) < (epoch - mask) * need:
+                return False
         needs_decision = int(t["type"]) == MS_UPDATE or (int(t["type"]) == MS_GEMM and int(t["flags"]) & F_FUSED_OPT)
         if needs_decision and mp.patience > 0 and (int(self.counters[ri][mp.decide_cnt]) >> 1) < epoch:
             return False
@@ -593,6 +617,11 @@ class MegaEmulator:
         if sc < 0:
             return
         self.counters[ri][sc] += 1
+        if sf >= 0 and self.plans[ri].xcnt:
+            for r in range(self.W):
+                if (sm >> r) & 1:
+                    self.plans[r].flags[XCNT_BASE + sf * CNT_STRIDE] += 1
+            return
         if sf >= 0 and self.counters[ri][sc] == epoch * tot:
             for r in range(self.W):
                 if (sm >> r) & 1:

@@ -35,7 +35,7 @@ def _ranks(model, crit, opt_cls, kw, W, B, patience=0, window=None, data=None, g
         numel = plan.fu.numel
         per = ((numel // 4 + W - 1) // W) * 4
         owned = (min(numel, per * r), min(numel, per * (r + 1)))
-        flags = torch.zeros(MS_MAX_FLAGS * 8, dtype=torch.int64)
+        flags = torch.zeros(4096, dtype=torch.int64)        # AR_FLAG_WORDS: epoch flags first, cross-GPU counters from word 1024
         mp = MegaPlan(plan, spec, patience, 0, owned, window, X.clone(), tgt, flags, grid=grid, chunk=chunk)
         assert mp.ok, mp.reason
         plans.append(plan)
