@@ -508,6 +508,7 @@ class MlpStep {
     p_.xcnt = 1;
     p_.mc_flags = reinterpret_cast<uint32_t*>(mc_flags_ptr);
   }
+  void set_sys_fence_all(bool on) { p_.sys_fence_all = on ? 1 : 0; }
   void set_prof_kb(const OptT& prof) {
     prof_kb_ = prof;
     if (prof) {
@@ -778,6 +779,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     int64_t, int64_t, int64_t, int64_t, int64_t, const Tensor&>())
       .def("set_prof", &MlpStep::set_prof)
       .def("set_xcnt", &MlpStep::set_xcnt)
+      .def("set_sys_fence_all", &MlpStep::set_sys_fence_all)
       .def("set_prof_kb", &MlpStep::set_prof_kb)
       .def("run", &MlpStep::run)
       .def("run_many", &MlpStep::run_many, py::call_guard<py::gil_scoped_release>())

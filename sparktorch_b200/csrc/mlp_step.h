@@ -121,6 +121,7 @@ struct MsParams {
   uint32_t* error;         // [4] device word set before a trap: code, cta, task, epoch
   int xcnt;                // 1: cross-GPU dependencies are counters (wait kind 3), tasks signal every consumer rank directly
   uint32_t* mc_flags;      // NVLS multicast alias of the symmetric flag block (null: one red per peer)
+  int sys_fence_all;       // 1: every cross-GPU flag is preceded by a system-scope fence (default: only the publication's)
 };
 
 int ms_smem_bytes();

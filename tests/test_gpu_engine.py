@@ -332,8 +332,6 @@ def test_fused_cnn_predictor_matches_eager():
     assert (out.argmax(1) == want.argmax(1)).mean() > 0.97
 
 
-@pytest.mark.skipif(os.environ.get("SPARKTORCH_PENDING_TESTS", "0") != "1",
-                    reason="written after the GPU budget of round 1 was spent - enable with SPARKTORCH_PENDING_TESTS=1 and promote once green")
 def test_hogwild_fused_cnn_worker_matches_sync_fused_on_one_gpu():
     """Same as the MLP variant, for the CNN plan: conv weights gathered through K-AG, split head, 'sweep' windows."""
     import copy
