@@ -25,6 +25,7 @@ sockets on 127.0.0.1.
 from __future__ import annotations
 
 import atexit
+import multiprocessing
 import os
 import queue
 import socket
@@ -136,7 +137,12 @@ class LocalCluster:
     def _ensure_listener(self) -> None:
         if self._listener is None:
             self._port = _free_port()
-            self._listener = Listener(("127.0.0.1", self._port), authkey=_AUTH)
+            # backlog: multiprocessing's default is 1.  Under torchrun the executors all read the port from the store and connect in
+            # the same instant; with a one-entry accept queue the kernel drops the overflowing handshakes, and a client whose final
+            # ACK was dropped believes it is connected and then waits for an authentication challenge that never comes, while
+            # the driver waits in accept() - the intermittent 8-rank start-up hang (stack dumps: profiles/hang_8gpu_startup.md)
+            backlog = int(os.environ.get("SPARKSHIM_LISTEN_BACKLOG", "0")) or max(128, 4 * self.n_slots)
+            self._listener = Listener(("127.0.0.1", self._port), backlog=backlog, authkey=_AUTH)
             if self.mode == "torchrun":
                 _publish_port(self._port)
 
@@ -159,8 +165,13 @@ class LocalCluster:
         pending = set(need)
         self._listener._listener._socket.settimeout(300.0)  # type: ignore[attr-defined]
         while pending:
-            conn = self._listener.accept()
-            slot = conn.recv()
+            try:
+                conn = self._listener.accept()          # includes the authentication handshake with that client
+                slot = conn.recv()
+            except TimeoutError:
+                raise RuntimeError(f"executors {sorted(pending)} did not connect to the driver within 300 s") from None
+            except (EOFError, OSError, multiprocessing.AuthenticationError):
+                continue                                # a client that gave up on a stale connection and is reconnecting
             self._slots[slot] = _Slot(slot, conn, procs.get(slot))
             pending.discard(slot)
 

@@ -689,6 +689,20 @@ int64_t flag_words() { return st::AR_FLAG_WORDS; }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "sparktorch_b200 native kernels (sm_100a)";
+  m.def("conv2d_fwd_implicit", [](const Tensor& x, const Tensor& w, Tensor& out, const c10::optional<Tensor>& bias, bool relu, int64_t R,
+                                  int64_t S, int64_t stride, int64_t pad, int64_t dil) {
+    TORCH_CHECK(x.is_cuda() && w.is_cuda() && out.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 &&
+                out.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.is_contiguous() && w.dim() == 2 && w.stride(1) == 1 && out.dim() == 2 &&
+                out.stride(1) == 1, "x: [N, H, W, C] bf16 contiguous; w: [Cout, R*S*C] bf16; out: [N*P*Q, Cout] bf16");
+    TORCH_CHECK(w.size(1) == R * S * x.size(3) && out.size(1) == w.size(0));
+    st::GemmEpilogue ep;
+    ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+    ep.ld_out = out.stride(0);
+    ep.relu = relu ? 1 : 0;
+    if (bias.has_value()) { TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kFloat && bias->numel() >= w.size(0)); ep.bias = bias->data_ptr<float>(); }
+    return int64_t(st::conv2d_fwd_implicit(x.data_ptr(), int(x.size(0)), int(x.size(1)), int(x.size(2)), int(x.size(3)), w.data_ptr(), w.stride(0),
+                                           int(w.size(0)), int(R), int(S), int(stride), int(pad), int(dil), &ep, 0, cur_stream()));
+  }, "forward convolution as an implicit GEMM (TMA im2col loads, tcgen05 MMA): returns 0, or -2 when the shape is not handled");
   m.def("gemm_bf16_2cta", [](const Tensor& A, const Tensor& B, Tensor& Cout, const c10::optional<Tensor>& bias, double alpha, bool relu) {
     TORCH_CHECK(A.is_cuda() && B.is_cuda() && Cout.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16 &&
                 Cout.scalar_type() == at::kBFloat16 && A.dim() == 2 && B.dim() == 2 && Cout.dim() == 2);

@@ -74,6 +74,18 @@ ST_DEVINL void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int3
 }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
+// im2col-mode TMA load (tensor map from cuTensorMapEncodeIm2col over [N, H, W, C]): `pixelsPerColumn` output pixels starting at the
+// receptive-field corner (w, h) of image n (walking w, then h, then n inside the bounding box), `channelsPerPixel` channels from c,
+// all shifted by the filter tap offset (off_w, off_h); positions outside the image read as 0.
+ST_DEVINL void tma_load_im2col_4d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c, int32_t w, int32_t h, int32_t n,
+                                  uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 ST_DEVINL void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
 }

@@ -340,7 +340,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + 64 * j, k0);
         } else {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0 + a_row_off);
+          if (win.flags & 8) {       // implicit-GEMM convolution: one filter tap x 64 channels of the tile's 128 output pixels
+            const int kb = kb_begin + i;
+            const int tap = kb / win.conv_cb, cb = kb - tap * win.conv_cb;
+            const int fr = tap / win.conv_S, fs = tap - fr * win.conv_S;
+            const int img = m0 / (win.conv_P * win.conv_Q), rem = m0 - img * (win.conv_P * win.conv_Q);
+            const int op = rem / win.conv_Q, oq = rem - op * win.conv_Q;
+            tma_load_im2col_4d(sa, &tmap_a, &full_bar[s], cb * BLOCK_K, oq * win.conv_stride - win.conv_pad, op * win.conv_stride - win.conv_pad,
+                               img, uint16_t(fs * win.conv_dil), uint16_t(fr * win.conv_dil));
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0 + a_row_off);
+          }
         }
         if constexpr (B_MN) {
 #pragma unroll
@@ -734,6 +744,38 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : int(r);
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                     const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// x [N, H, W, C] bf16 (dense NHWC) as an im2col tensor map: boxes of 128 output pixels x 64 channels, 128B swizzle, zero fill.
+// Bounding box: lower corner = -pad, upper corner = pad - (filter - 1) * dilation, so that the box walk visits exactly the
+// P x Q receptive-field corners of every image; the filter tap is added per load (instruction offsets).
+static int make_tmap_im2col_bf16(CUtensorMap* map, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad, int dil) {
+  static PFN_encodeIm2col enc = nullptr;
+  if (enc == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) != cudaSuccess || p == nullptr) return -1;
+    enc = reinterpret_cast<PFN_encodeIm2col>(p);
+  }
+  cuuint64_t gdim[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+  cuuint64_t gstride[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  int lower[2] = {-pad, -pad};                                          // (w, h)
+  int upper[2] = {pad - (S - 1) * dil, pad - (R - 1) * dil};
+  cuuint32_t estr[4] = {1, cuuint32_t(stride), cuuint32_t(stride), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstride, lower, upper, BLOCK_K, BLOCK_M, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return int(r);
+  // (driver quirk handled the way CUTLASS does - cute/atom/copy_traits_sm90_im2col.hpp: descriptors of tensors below 128 KB get
+  //  a bit set by drivers <= 13.1 that the im2col unit then trips over)
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && int64_t(N) * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return 0;
+}
+
 // Tile width: the smallest power of two covering N, then shrunk further until ~64 CTAs are in
 // flight (tiny problems are bound by how much ONE SM can pull from L2, so they want many small
 // tiles); big problems keep 128-wide tiles.
@@ -862,6 +904,30 @@ int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, 
   else if (a_mn) e = dispatch_bn<true, false>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
   else if (b_mn) e = dispatch_bn<false, true>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
   else e = dispatch_bn<false, false>(block_n, ta, tb, *ep, win, peer, M, N, K, split_k, stream);
+  return e == cudaSuccess ? 0 : 1000 + int(e);
+}
+
+int conv2d_fwd_implicit(const void* x, int N, int H, int W, int C, const void* w, int64_t ldw, int Cout, int R, int S, int stride, int pad,
+                        int dil, const GemmEpilogue* ep, int block_n, cudaStream_t stream) {
+  if (C % BLOCK_K != 0 || stride < 1 || stride > 8 || dil < 1 || R < 1 || S < 1) return -2;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (ldw & 7)) return -2;
+  const int P = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1, Q = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  if (P < 1 || Q < 1 || pad > 127 || (S - 1) * dil - pad > 128 || (R - 1) * dil - pad > 128) return -2;
+  const int64_t M64 = int64_t(N) * P * Q;
+  if (M64 > (int64_t(1) << 30)) return -2;
+  const int M = int(M64), K = R * S * C;
+  if (ep->loss_kind != 0) return -5;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_im2col_bf16(&ta, x, N, H, W, C, R, S, stride, pad, dil);
+  if (rc) return rc;
+  if (block_n <= 0) block_n = gemm_pick_block_n(M, Cout, 0);
+  rc = make_tmap_bf16_2d(&tb, w, uint64_t(Cout), uint64_t(K), uint64_t(ldw), uint32_t(block_n));
+  if (rc) return rc;
+  GemmWindow win{};
+  win.flags = 8;
+  win.conv_cb = C / BLOCK_K; win.conv_S = S; win.conv_P = P; win.conv_Q = Q; win.conv_stride = stride; win.conv_pad = pad; win.conv_dil = dil;
+  GemmPeerB peer{};
+  cudaError_t e = dispatch_bn<false, false>(block_n, ta, tb, *ep, win, peer, M, Cout, K, 1, stream);
   return e == cudaSuccess ? 0 : 1000 + int(e);
 }
 

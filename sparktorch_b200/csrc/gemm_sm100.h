@@ -70,8 +70,18 @@ struct GemmWindow {
   const StepState* state = nullptr;
   int64_t window_rows = 0;
   int64_t n_windows = 1;
-  int flags = 0;                          // 1: offset A rows (K-major A), 2: offset B's K rows (MN-major B), 4: offset labels/targets
+  int flags = 0;                          // 1: offset A rows (K-major A), 2: offset B's K rows (MN-major B), 4: offset labels/targets,
+                                          // 8: implicit-GEMM convolution - A is an NHWC activation tensor behind an im2col tensor map
+  // flags & 8: k-block kb = filter tap kb / conv_cb (r = tap / conv_S, s = tap % conv_S), channels [64 * (kb % conv_cb), +64);
+  // the tile's first output pixel m0 = (n, p, q) in an image of conv_P x conv_Q output pixels
+  int conv_cb = 0, conv_S = 0, conv_P = 0, conv_Q = 0, conv_stride = 1, conv_pad = 0, conv_dil = 1;
 };
+
+// Forward convolution as an implicit GEMM: out[N*P*Q, Cout] = act(patches(x) W^T + bias), the patch matrix never exists - the
+// TMA unit gathers 128 output pixels x 64 channels of one filter tap per k-block straight from x [N, H, W, C] (im2col tensor map).
+// w: [Cout, R*S*C] bf16 with the reduction index ordered (r, s, c).  C % 64 == 0, square padding / stride / dilation.
+int conv2d_fwd_implicit(const void* x, int N, int H, int W, int C, const void* w, int64_t ldw, int Cout, int R, int S, int stride, int pad,
+                        int dil, const GemmEpilogue* ep, int block_n, cudaStream_t stream);
 
 int gemm_pick_block_n(int M, int N, int b_mn);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);

@@ -185,10 +185,33 @@ def _conv_ok(m: nn.Conv2d) -> bool:
             and not isinstance(m.padding, str) and m.padding_mode == "zeros" and type(m) is nn.Conv2d)
 
 
+def _conv_forward_implicit(self, x, stride: int, padding: int):
+    """Forward-only convolution (inference / validation) as an implicit GEMM: the TMA unit gathers the patches (im2col tensor
+    map over the NHWC activations), no patch matrix is written (csrc/gemm_sm100.cu conv2d_fwd_implicit).  Returns None when the
+    layer is not eligible (C_in % 64 != 0) so the caller falls back to the explicit path."""
+    C = native.load(required=True)
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = self.weight.shape
+    if Cin % 64 != 0 or not hasattr(C, "conv2d_fwd_implicit"):
+        return None
+    OH, OW = (H + 2 * padding - kh) // stride + 1, (W + 2 * padding - kw) // stride + 1
+    xn = x.detach().to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()                      # NHWC
+    wk = self._st_cache.get(self.weight.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin), self.weight._version, ("rsc", _STEP_STAMP[0]))
+    out = torch.empty(B * OH * OW, _pad(Cout), dtype=torch.bfloat16, device=x.device)[:, :Cout]
+    rc = C.conv2d_fwd_implicit(xn, wk, out, self.bias.detach().float() if self.bias is not None else None, False, kh, kw, stride, padding, 1)
+    if rc != 0:
+        return None
+    return out.reshape(B, OH, OW, Cout).permute(0, 3, 1, 2).to(x.dtype)
+
+
 def _conv_forward(self, x):
     if not x.is_cuda or x.dim() != 4 or x.numel() == 0:
         return self._conv_forward(x, self.weight, self.bias)
     one = lambda v: v[0] if isinstance(v, (tuple, list)) else v      # noqa: E731
+    if not torch.is_grad_enabled() or not (x.requires_grad or self.weight.requires_grad):
+        y = _conv_forward_implicit(self, x, one(self.stride), one(self.padding))
+        if y is not None:
+            return y
     return _Conv2dFn.apply(x, self.weight, self.bias, self._st_cache, one(self.stride), one(self.padding))
 
 
