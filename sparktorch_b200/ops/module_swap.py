@@ -21,6 +21,8 @@ that goes back to the driver loads into the user's original module.
 """
 from __future__ import annotations
 
+import os
+
 import types
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -189,6 +191,10 @@ def _conv_forward_implicit(self, x, stride: int, padding: int):
     """Forward-only convolution (inference / validation) as an implicit GEMM: the TMA unit gathers the patches (im2col tensor
     map over the NHWC activations), no patch matrix is written (csrc/gemm_sm100.cu conv2d_fwd_implicit).  Returns None when the
     layer is not eligible (C_in % 64 != 0) so the caller falls back to the explicit path."""
+    # opt-in (SPARKTORCH_IMPLICIT_CONV=1): the kernel builds (SASS: UTMALDG.4D.IM2COL) and the host-side geometry is covered by a
+    # CPU test, but the round's GPU budget ran out before its first run on a B200 - bench/conv_implicit_check.py is that run
+    if os.environ.get("SPARKTORCH_IMPLICIT_CONV", "0") != "1":
+        return None
     C = native.load(required=True)
     B, Cin, H, W = x.shape
     Cout, _, kh, kw = self.weight.shape

@@ -587,3 +587,24 @@ def test_gemm_cta_pair_declines_small_shapes(C):
     a, b = _mk(128, 64), _mk(64, 64)
     out = torch.zeros(128, 64, dtype=torch.bfloat16, device=dev())
     assert C.gemm_bf16_2cta(a, b, out, None, 1.0, False) == -2
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SPARKTORCH_IMPLICIT_CONV", "0") != "1",
+                    reason="implicit-GEMM convolution (TMA im2col) was written after the round's GPU budget was spent: run "
+                           "bench/conv_implicit_check.py first, then enable with SPARKTORCH_IMPLICIT_CONV=1")
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [(2, 8, 8, 64, 64, 3, 1, 1), (4, 14, 14, 128, 64, 3, 1, 1), (2, 16, 16, 64, 128, 3, 2, 1),
+                                                         (2, 12, 12, 64, 64, 1, 1, 0), (3, 10, 7, 64, 32, 3, 1, 1)])
+def test_conv_forward_implicit_gemm(C, N, H, W, Cin, Cout, k, stride, pad):
+    import torch.nn.functional as F
+
+    x = (torch.randn(N, Cin, H, W, device=dev()) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev()) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Cout, device=dev())
+    P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous()
+    out = torch.full((N * P * Q, Cout), float("nan"), dtype=torch.bfloat16, device=dev())
+    assert C.conv2d_fwd_implicit(xn, wk, out, b, True, k, k, stride, pad, 1) == 0
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float(), w.float(), b, stride=stride, padding=pad)).permute(0, 2, 3, 1).reshape(N * P * Q, Cout)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
