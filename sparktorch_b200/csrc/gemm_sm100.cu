@@ -875,7 +875,8 @@ int gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, 
   if (g_pair_mode != 0 && !a_mn && !b_mn && peer.world == 0 && win.flags == 0 && split_k == 1 && ep->out_bf16 != nullptr &&
       ep->mask_src == nullptr && ep->out_t_bf16 == nullptr && ep->out_f32 == nullptr && ep->out_t_f32 == nullptr && ep->colsum == nullptr &&
       ep->colsumsq == nullptr && ep->loss_kind == 0 && ep->push_world == 0 && ep->prof == nullptr && M >= 512 && N >= 256 && K >= 256 &&
-      int64_t(M) * N >= (int64_t(1) << 20) && (ep->ld_out & 7) == 0) {
+      // (enough 256 x 256 tiles to keep most of the 74 pairs busy: below that the single-CTA kernels' smaller tiles spread further)
+      int64_t((M + 255) / 256) * ((N + 255) / 256) >= 48 && (ep->ld_out & 7) == 0) {
     const int rc2 = gemm_bf16_2cta(A, lda, B, ldb, ep->out_bf16, ep->ld_out, M, N, K, ep->bias, ep->alpha, ep->relu, stream);
     if (rc2 != -2) return rc2;
   }
