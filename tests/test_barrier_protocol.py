@@ -91,3 +91,77 @@ def test_checker_catches_a_broken_protocol():
     # overwrite gradients that are still being read
     r = _explore(2, 3, shared_phase_slot=True)
     assert r["violations"] or r["deadlocks"]
+
+
+# ------------------------------------------------------------------------------------------------ one-shot push exchange
+def _explore_push(world: int, epochs: int, n_slots: int = 2):
+    """The push / LL-style exchange (csrc/comm_ar.cu allreduce_push_update_kernel, SPARKTORCH_EXCHANGE=push): the GEMM epilogues of
+    step e mirror the rank's gradients into its receive slot (parity e % n_slots) on EVERY peer, ONE flag exchange says "my pushes
+    of step e are complete", then every operand of the reduction is local.  There is no second barrier: what protects a slot that
+    a slow rank is still reading from the pushes of step e + n_slots is that a rank reaches that step only after the flag exchange
+    of step e + 1, which the slow rank enters after its reads.  The checker explores all interleavings; with a single slot
+    (n_slots = 1) the same program must be caught overwriting live data."""
+    progs = []
+    for me in range(world):
+        peers = [p for p in range(world) if p != me]
+        ops = []
+        for e in range(1, epochs + 1):
+            for p in peers:
+                ops.append(("push", p, e % n_slots, e))          # slot[p][parity][me] = e
+            for p in peers:
+                ops.append(("set_flag", p, e))
+            for p in peers:
+                ops.append(("wait_flag", p, e))
+            for p in peers:
+                ops.append(("read_slot", p, e % n_slots, e))      # slot[me][parity][p] must hold e
+        progs.append(ops)
+    pairs = [(d, s) for d in range(world) for s in range(world) if s != d]
+    fidx = {k: i for i, k in enumerate(pairs)}
+    skeys = [(d, par, s) for d in range(world) for par in range(n_slots) for s in range(world) if s != d]
+    sidx = {k: i for i, k in enumerate(skeys)}
+    start = (tuple(0 for _ in range(world)), tuple(0 for _ in pairs), tuple(0 for _ in skeys))
+    seen, stack = {start}, [start]
+    violations, deadlocks, finals = [], 0, 0
+    while stack:
+        pcs, flags, slots = stack.pop()
+        if all(pcs[r] == len(progs[r]) for r in range(world)):
+            finals += 1
+            continue
+        moved = False
+        for r in range(world):
+            if pcs[r] == len(progs[r]):
+                continue
+            op = progs[r][pcs[r]]
+            nflags, nslots = flags, slots
+            if op[0] == "push":
+                i = sidx[(op[1], op[2], r)]
+                nslots = slots[:i] + (op[3],) + slots[i + 1:]
+            elif op[0] == "set_flag":
+                i = fidx[(op[1], r)]
+                nflags = flags[:i] + (max(flags[i], op[2]),) + flags[i + 1:]
+            elif op[0] == "wait_flag":
+                if flags[fidx[(r, op[1])]] < op[2]:
+                    continue
+            elif op[0] == "read_slot":
+                if slots[sidx[(r, op[2], op[1])]] != op[3]:
+                    violations.append((r, op))
+            moved = True
+            nxt = (pcs[:r] + (pcs[r] + 1,) + pcs[r + 1:], nflags, nslots)
+            if nxt not in seen:
+                seen.add(nxt)
+                stack.append(nxt)
+        if not moved:
+            deadlocks += 1
+    return dict(states=len(seen), violations=violations, deadlocks=deadlocks, finals=finals)
+
+
+@pytest.mark.parametrize("world,epochs", [(2, 4), (3, 3)])
+def test_one_shot_push_exchange_needs_no_second_barrier(world, epochs):
+    r = _explore_push(world, epochs, n_slots=2)
+    assert r["deadlocks"] == 0 and r["finals"] >= 1 and r["states"] > 50
+    assert not r["violations"], r["violations"][:3]
+
+
+def test_push_exchange_with_a_single_receive_slot_is_caught():
+    r = _explore_push(2, 3, n_slots=1)
+    assert r["violations"], "a fast rank's pushes of step e+1 must be seen overwriting the slot a slow rank still reads"
