@@ -15,7 +15,7 @@
 // counters in global memory (within the GPU) and epoch flags in symmetric memory (across GPUs); nothing
 // is ever reset, a wait is "counter >= epoch * need".  A CTA is warp specialised like the stand-alone
 // GEMM (gemm_sm100.cu): warp 0 waits for a task's inputs and streams its operand tiles with TMA through
-// an 8-stage mbarrier ring, warp 1 issues tcgen05.mma into a double-buffered TMEM accumulator, warps 2-5
+// an 8-stage mbarrier ring, warp 1 issues tcgen05.mma into a double-buffered TMEM accumulator, warps 2-9
 // drain TMEM, run the fused epilogue, publish the tile and signal its consumers - so the epilogue of task
 // t overlaps the operand loads and MMAs of task t+1.  Activations / dZ are double buffered by step
 // parity; together with "forward of layer l waits for the publication of W_l" that makes every
@@ -25,7 +25,14 @@
 // instructions (UTCHMMA, UTMALDG, UTCBAR) must be issued from warp-UNIFORM code (whole warp runs the loop,
 // `elect.sync` picks the issuing lane) - from a `lane == 0` branch every one of them is wrapped in an
 // R2UR waterfall loop; and the code must stay small - 300 KB of fully unrolled epilogues missed the
-// instruction cache on every task.  Hence the rolled 8-column epilogue below.
+// instruction cache on every task.  Hence the rolled 8-column epilogue below (and the few hot shapes as lean templates).
+//
+// Later cuts, each kept only after the kernel's own timeline showed the gain (profiles/round2_summary.md):
+//   chained head   the CTAs of the last layer's dgrad tiles recompute the head of their rows (logits, loss, dZ_L) and feed
+//                  dZ_L to the dgrad MMA through shared memory (MS_CHAIN_HEAD / MS_QUIET / MS_CHAIN_TAIL): one phase less;
+//   windows        a backward tile is run by two CTAs that drain half of its columns each (ep_c0 / ep_cols);
+//   early A        first-layer tiles load the batch before their weights are published (MS_EARLY_A);
+//   fences         consumers acquire at gpu scope; only the publication's flag is preceded by a system-scope fence.
 #include <cstddef>
 
 #include "common.cuh"

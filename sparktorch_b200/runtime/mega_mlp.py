@@ -9,6 +9,8 @@
     G_l    wgrad tiles        dW_l = dZ_l^T A_{l-1}  -> symmetric gradient arena (plain stores)
     U_s    update chunks      owner reduces its shard over the replicas (NVLS / peer loads), Adam/SGD,
                               publishes fp32 + bf16 to every replica
+    H_L    quiet head copies  (chained head) the B_L tiles' CTAs recompute logits / dZ_L of their rows and hand dZ_L to the
+                              dgrad MMA through shared memory; nothing is stored or signalled - F_L keeps that job
 
 Dependencies are monotonic counters (inside a GPU) and epoch flags (between GPUs); see the kernel's header
 comment.  The reference loop this replaces: /root/reference/sparktorch/distributed.py:140-203.
