@@ -300,6 +300,14 @@ def run_ours(args):
         k = max(1, min(3, len(tl) // 2))
         return loss_record(sum(tl[:k]) / k, sum(tl[-k:]) / k) if tl else loss_record(None, None)
 
+    def launches_of(hist):
+        """kernels of ours launched inside the timed region: the K-STEP kernel runs several steps per launch"""
+        per = hist.get("gpu_launches_per_step", 0)
+        sk = hist.get("step_kernel")
+        if sk and sk.get("steps_per_launch", 1) > 1:
+            return int(per * -(-args.steps // sk["steps_per_launch"]))
+        return int(per * args.steps)
+
     gb = args.batch * args.gpus
     dev_ms = h["window_ms"]["device_ms"]
     value = gb * args.steps / (dev_ms / 1e3)
@@ -316,7 +324,7 @@ def run_ours(args):
                           f": resident partition {rows}x{IN_FEATURES} per GPU "
                           f"({rows * IN_FEATURES * 2 / 2**20:.0f} MiB bf16 vs 126 MiB L2) swept by mini-batches; "
                           "weights/optimizer state stay cache resident as in any training loop")},
-        "gpu_launches": int(h.get("gpu_launches_per_step", 0) * args.steps),
+        "gpu_launches": launches_of(h),
         "loss": loss_of(h),
         "step_kernel": h.get("step_kernel"),
         "clocks": clock_summary(h),
@@ -327,7 +335,7 @@ def run_ours(args):
                       "h2d_bytes_per_step": he.get("h2d_bytes_per_step", 0),
                       "d2h_bytes_per_step": he.get("d2h_bytes_per_step", 0),
                       "ms_per_step": e_ms / args.steps, "engine": he.get("engine"),
-                      "gpu_launches": int(he.get("gpu_launches_per_step", 0) * args.steps),
+                      "gpu_launches": launches_of(he),
                       "loss": loss_of(he), "clocks": clock_summary(he)}
     emit(out)
     spark.stop()
