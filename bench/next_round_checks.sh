@@ -1,18 +1,24 @@
 #!/bin/bash
-# First GPU minutes of the next round (things written or left open after round 1's GPU budget ran out).
+# What the end of round 2 left unrun (GPU budget spent) - run these first, in this order.
+#   gpurun --timeout 900 -- 'bash bench/next_round_checks.sh 1'        (one GPU)
 #   gpurun --gpus 8 --timeout 400 -- 'bash bench/next_round_checks.sh 8'
-N=${1:-8}
+N=${1:-1}
 mkdir -p gpurun_out
-tr() { port=$1; shift; timeout ${T:-120} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port "$@"; }
-echo "=== 1. open bug: synchronous CNN at $N GPUs - a stall now aborts with a thread dump after 45 s"
-SPARKTORCH_STALL_TIMEOUT_S=45 T=150 tr 29701 bench.py --gpus $N --model cnn --steps 100 --warmup 10 --no-e2e > gpurun_out/cnn_sync_n$N.log 2>&1
-echo "rc=$?"; grep -E "^\{|no progress|Error|error" gpurun_out/cnn_sync_n$N.log | head -20 | cut -c1-300
-echo "    same without PDL / without NVLS (one of them passing localises the problem)"
-SPARKTORCH_PDL=0 SPARKTORCH_STALL_TIMEOUT_S=45 T=150 tr 29702 bench.py --gpus $N --model cnn --steps 100 --warmup 10 --no-e2e 2>&1 | grep -E "^\{|no progress" | cut -c1-200
-SPARKTORCH_NVLS=0 SPARKTORCH_STALL_TIMEOUT_S=45 T=150 tr 29703 bench.py --gpus $N --model cnn --steps 100 --warmup 10 --no-e2e 2>&1 | grep -E "^\{|no progress" | cut -c1-200
-echo "=== 2. multi-GPU correctness script (thresholds for 8 asynchronous workers were set without a run)"
-T=300 tr 29704 tests/multi_gpu_check.py > gpurun_out/mgc_next_n$N.log 2>&1; echo "rc=$?"; grep -E "OK|Error|assert" gpurun_out/mgc_next_n$N.log | head
-echo "=== 3. pending single-GPU tests"
-SPARKTORCH_PENDING_TESTS=1 timeout 200 python -m pytest -m gpu -q -p no:cacheprovider tests/test_gpu_engine.py -k "hogwild_fused_cnn" 2>&1 | tail -3
-echo "=== 4. compute-sanitizer over the kernel tests (single GPU)"
-timeout 600 bash bench/sanitize.sh 2>&1 | tail -15
+if [ "$N" = "1" ]; then
+  echo "=== implicit-GEMM convolution (TMA im2col): numerics with convention diagnostics, then timing vs explicit im2col+GEMM and cuDNN"
+  timeout 300 python bench/conv_implicit_check.py 2>&1 | tail -25
+  echo "=== its GPU test (opt-in until the line above is green)"
+  SPARKTORCH_IMPLICIT_CONV=1 timeout 200 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k implicit 2>&1 | tail -3
+  echo "=== full GPU suite (last full run predates the CTA-pair dispatch in gemm_bf16)"
+  timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -6
+  echo "=== headline bench, driver arguments"
+  timeout 200 python bench.py --steps 20 --warmup 5 | tail -1 | cut -c1-400
+  echo "=== ResNet-50 bf16 step with the CTA-pair GEMM in the forward convolutions"
+  timeout 400 python bench.py --model resnet50 --steps 10 --warmup 3 2>&1 | tail -1 | cut -c1-400
+else
+  tr() { port=$1; shift; timeout ${T:-150} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port "$@"; }
+  echo "=== start-up of the Spark stand-in at $N ranks, 3 times (the round-1/2 hang: profiles/hang_8gpu_startup.md)"
+  for rep in 1 2 3; do T=120 tr $((29800+rep)) bench.py --gpus $N --steps 20 --warmup 5 --no-e2e 2>gpurun_out/start_$rep.err | tail -1 | cut -c1-200; done
+  echo "=== headline bench at $N GPUs with the final K-STEP build"
+  T=150 tr 29810 bench.py --gpus $N --steps 200 --warmup 20 | tail -1 | cut -c1-600
+fi
