@@ -84,6 +84,10 @@ class Server:
         handler = _make_handler(self)
         ThreadingHTTPServer.daemon_threads = True
         ThreadingHTTPServer.allow_reuse_address = True
+        # every hogwild worker pulls / pushes once per iteration, all at about the same time: socketserver's default listen backlog
+        # of 5 overflows with more than a handful of partitions (dropped handshakes = multi-second stalls, see
+        # profiles/hang_8gpu_startup.md for what a backlog of 1 did to the executor start-up)
+        ThreadingHTTPServer.request_queue_size = 256
         self._httpd = ThreadingHTTPServer(("0.0.0.0", self.port), handler)
         self.port = self._httpd.server_address[1]
         self._thread = threading.Thread(target=self._httpd.serve_forever, name="sparktorch-ps", daemon=True)
