@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sorted(glob.glob(os.path.join(ROOT, "sparktorch_b200", "_C*.so")))[0]
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 COLS = [("UTCHMMA", "UTCHMMA (tcgen05.mma)"), ("UTMALDG", "UTMALDG (TMA load)"), ("LDTM", "LDTM (tcgen05.ld)"),
+        ("UTMASTG", "UTMASTG (TMA store)"), ("\\.2CTA", ".2CTA (cta_group::2)"), ("IM2COL", "IM2COL (TMA im2col load)"),
         ("UTCBAR", "UTCBAR (tcgen05.commit)"), ("SYNCS", "SYNCS (mbarrier)"), ("MULTIMEM|LDGMC|STGMC|REDGMC", "multimem (NVLS)"),
         ("MEMBAR\\.\\S*SYS", "MEMBAR.SYS"), ("\\bRED\\b|\\bATOM|\\bATOMG|\\bREDG|\\bATOMS", "ATOM/RED"), ("ACQBULK|GRIDDEP|ACQBLK", "griddepcontrol"),
         ("SHFL", "SHFL"), ("\\bSTG", "STG")]
@@ -35,7 +36,7 @@ if cur:
 
 def pretty(name: str) -> str:
     out = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip() or name
-    out = re.sub(r"^void ", "", out)
+    out = re.sub(r"^void ", "", out).replace("(anonymous namespace)::", "")
     out = re.sub(r"\(.*", "", out)
     return out.replace("st::", "")
 
